@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- BFV ct x ct mul+relinearize throughput at N=2^15, 14x62-bit q (BASELINE.json).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--batch B]
+
+A "step" is one pass of Multiplicator::multiply over one batch of `--batch` ciphertext pairs
+per GPU (synthetic uniform residues, as fresh BFV ciphertext halves are).  Prints ONE JSON line
+(rank 0).  `--impl reference` times the reference's CPU algorithm instead (the oracle port --
+the Rust reference cannot be built in this image), on all host cores, same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEGREE = 1 << 15
+N_MODULI = 14
+PLAINTEXT = 786433          # generate_prime(20, 2N, 2^20), as benches/bfv.rs:28 does
+NTT_CFG = dict(degree=1 << 14, n_moduli=8, batch=256)   # BASELINE config 2
+METRIC = "bfv_ct_mul_relin_per_sec_n32768_14x62bit"
+UNIT = "products/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+class DevArray:
+    """__cuda_array_interface__ view of a batch's device storage (zero-copy fill from torch)."""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+def fill_uniform(torch, ct, moduli, seed):
+    """uniform residues in [0, q_i) written straight into the batch's HBM storage"""
+    count, parts, limbs, n = ct.shape()
+    view = torch.as_tensor(DevArray(ct.device_ptr(), count * parts * limbs * n), device="cuda").view(
+        count, parts, limbs, n)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    for i, q in enumerate(moduli[:limbs]):
+        view[:, :, i, :].copy_(torch.randint(0, q, (count, parts, n), dtype=torch.int64, device="cuda", generator=g))
+    torch.cuda.synchronize()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; kind 'port'), all host cores,
+    one ciphertext pair per worker per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    workers = max(1, min(cores, 32))
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(workers + 1)
+    q = ctx.Queue()
+
+    def worker(idx):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import numpy as np
+        import fhe_oracle as O
+        rng = np.random.default_rng(1000 + idx)
+        par = O.BfvParameters(DEGREE, PLAINTEXT, moduli_sizes=[62] * N_MODULI)
+        ctxq = par.context_at_level(0)
+        def rnd(shape_parts):
+            a = np.zeros((shape_parts, N_MODULI, DEGREE), np.uint64)
+            for i, qq in enumerate(ctxq.moduli):
+                a[:, i, :] = rng.integers(0, qq, size=(shape_parts, DEGREE), dtype=np.uint64)
+            return a
+        ksk = O.KeySwitchingKey.from_arrays(par, rnd(N_MODULI), rnd(N_MODULI))
+        m = O.Multiplicator.default(O.RelinearizationKey.from_ksk(ksk))
+        a = O.Ciphertext.from_array(par, rnd(2), 0)
+        b = O.Ciphertext.from_array(par, rnd(2), 0)
+        for _ in range(args.warmup + args.steps):
+            barrier.wait()
+            m.multiply(a, b)
+            barrier.wait()
+        q.put(idx)
+
+    procs = [ctx.Process(target=worker, args=(i,)) for i in range(workers)]
+    for p in procs:
+        p.start()
+    times = []
+    for s in range(args.warmup + args.steps):
+        barrier.wait()
+        t0 = time.perf_counter()
+        barrier.wait()
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    for p in procs:
+        p.join()
+    total = sum(times)
+    value = workers * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: n=2^15, 14x62-bit moduli, ct x ct mul + relinearize",
+                   "batch_per_step": workers},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": "%d steps x %d products (one per worker process), C oracle of the reference "
+                                   "algorithm (the Rust reference cannot be built here)" % (args.steps, workers)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample():
+    """single-thread oracle port on a bounded sample (3 products at the full size)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import fhe_oracle as O
+    rng = np.random.default_rng(5)
+    par = O.BfvParameters(DEGREE, PLAINTEXT, moduli_sizes=[62] * N_MODULI)
+    ctxq = par.context_at_level(0)
+
+    def rnd(parts):
+        a = np.zeros((parts, N_MODULI, DEGREE), np.uint64)
+        for i, qq in enumerate(ctxq.moduli):
+            a[:, i, :] = rng.integers(0, qq, size=(parts, DEGREE), dtype=np.uint64)
+        return a
+    ksk = O.KeySwitchingKey.from_arrays(par, rnd(N_MODULI), rnd(N_MODULI))
+    m = O.Multiplicator.default(O.RelinearizationKey.from_ksk(ksk))
+    a, b = O.Ciphertext.from_array(par, rnd(2), 0), O.Ciphertext.from_array(par, rnd(2), 0)
+    m.multiply(a, b)  # warm tables / page-in
+    n, t0 = 3, time.perf_counter()
+    for _ in range(n):
+        m.multiply(a, b)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d ct x ct mul+relin at n=2^15, 14x62-bit, single thread, C oracle of the reference "
+                      "algorithm (Rust reference not buildable here)" % n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("FHE_BENCH_BATCH", "1024")))
+    ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("FHE_BENCH_E2E_BATCH", "256")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import fhe_rs_b200 as F
+    L = F._capi.lib()
+
+    # BfvParametersBuilder::set_moduli_sizes(&[62; 14]) -> the library generates the primes (parameters.rs:391)
+    par = F.BfvParameters(DEGREE, PLAINTEXT, moduli_sizes=[62] * N_MODULI, device=local)
+    moduli = par.moduli()
+    B = args.batch
+    # independent ciphertexts shard across ranks: every rank owns B pairs (weak scaling), keys replicated
+    A = F.Ciphertext(par, B, 2)
+    Bt = F.Ciphertext(par, B, 2)
+    fill_uniform(torch, A, moduli, 1 + 2 * rank)
+    fill_uniform(torch, Bt, moduli, 2 + 2 * rank)
+    rng = np.random.default_rng(7)   # same key on every rank
+    kc = np.zeros((2, N_MODULI, N_MODULI, DEGREE), np.uint64)
+    for i, q in enumerate(moduli):
+        kc[:, :, i, :] = rng.integers(0, q, size=(2, N_MODULI, DEGREE), dtype=np.uint64)
+    rk = F.RelinearizationKey.from_arrays(par, kc[0], kc[1])
+    mult = F.Multiplicator.default(rk)
+    out = F.Ciphertext(par, B, 2)
+
+    def step():
+        F.check(L.fhe_b200_mul_relin(A._h, Bt._h, rk.ksk._h, 0, out._h, None))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.fhe_b200_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = L.fhe_b200_launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public host API with HOST buffers (pinned), copies inside the timed region
+    Be = min(args.e2e_batch, B)
+    words = Be * 2 * N_MODULI * DEGREE
+    ha = torch.empty(words, dtype=torch.int64).pin_memory()
+    hb = torch.empty(words, dtype=torch.int64).pin_memory()
+    ho = torch.empty(words, dtype=torch.int64).pin_memory()
+    ga = torch.as_tensor(DevArray(A.device_ptr(), words), device="cuda")
+    ha.copy_(ga); hb.copy_(torch.as_tensor(DevArray(Bt.device_ptr(), words), device="cuda"))
+    torch.cuda.synchronize()
+    Ae, Bte, oute = F.Ciphertext(par, Be, 2), F.Ciphertext(par, Be, 2), F.Ciphertext(par, Be, 2)
+
+    def e2e_step():
+        F.check(L.fhe_b200_batch_upload(Ae._h, 0, Be, ha.data_ptr(), None))
+        F.check(L.fhe_b200_batch_upload(Bte._h, 0, Be, hb.data_ptr(), None))
+        F.check(L.fhe_b200_mul_relin(Ae._h, Bte._h, rk.ksk._h, 0, oute._h, None))
+        F.check(L.fhe_b200_batch_download(oute._h, 0, Be, ho.data_ptr(), None))   # synchronises
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * e2e_steps / float(e2e_s.item())
+
+    # ---- roofline of the dominant kernel family (NTT), BASELINE config 2: [256][8][2^14] forward + inverse
+    roof = None
+    if rank == 0:
+        par2 = F.BfvParameters(NTT_CFG["degree"], PLAINTEXT, moduli_sizes=[62] * NTT_CFG["n_moduli"], device=local)
+        nm = par2.moduli()
+        X = F.Ciphertext(par2, NTT_CFG["batch"], 1, repr=F.POWER_BASIS)
+        fill_uniform(torch, X, nm, 99)
+        for _ in range(3):
+            X.into_ntt(); X.into_power_basis()
+        torch.cuda.synchronize()
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            X.into_ntt(); X.into_power_basis()
+        e1.record()
+        torch.cuda.synchronize()
+        ntt_ms = e0.elapsed_time(e1) / (2 * reps)
+        rows = NTT_CFG["batch"] * NTT_CFG["n_moduli"]
+        alg_bytes = 16.0 * NTT_CFG["degree"] * rows          # 16*N bytes per limb-NTT
+        achieved = alg_bytes / (ntt_ms * 1e-3) / 1e9
+        peak, how = peaks()
+        roof = {"bound": "hbm", "kernel": "ntt_cols_kernel+ntt_rows_kernel (one batched %d-row NTT, N=2^14)" % rows,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
+                "traffic": None, "ms_per_launch": ntt_ms,
+                "note": "algorithmic bytes = 16*N per limb-NTT (SURVEY 8d); the transform is integer-issue bound "
+                        "(about 28 integer instr per 62-bit Shoup butterfly), see DESIGN.md"}
+
+    if rank == 0:
+        cpu = None if args.no_cpu_baseline else cpu_baseline_sample()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: n=2^15, 14x62-bit moduli, ct x ct mul + relinearize, "
+                                   "batch %d ciphertext pairs per GPU" % B,
+                       "batch_per_gpu": B, "parallelism": "independent ciphertexts sharded per rank, keys replicated",
+                       "l2": "inputs (%.1f GB per step per GPU) exceed L2, no flush needed" % (2 * B * 7.34e-3)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * words * 8,
+                    "d2h_bytes_per_step": words * 8, "batch": Be},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

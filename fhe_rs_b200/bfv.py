@@ -1,0 +1,434 @@
+"""Host-side mirror of the reference's `fhe::bfv` interface for the accelerated path
+(BfvParameters, Ciphertext, Multiplicator, RelinearizationKey, GaloisKey / EvaluationKey),
+implemented purely on top of the C ABI in include/fhe_b200.h.
+
+Same names, argument meaning and error behaviour as the reference items cited in each
+docstring (paths relative to /root/reference/crates).  Differences forced by the device:
+a `Ciphertext` here is a *batch* of ciphertexts of one level resident in HBM (the reference's
+operators act on one ciphertext; per-ciphertext FFI would be launch/PCIe bound),
+and keys are constructed from their NTT-domain words (as after deserialization,
+key_switching_key.rs:418-482) -- key generation is client-side code outside this path.
+No CPU fallback exists: every operation is a CUDA launch behind the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import NTT, POWER_BASIS, FheError, check
+
+__all__ = ["BfvParameters", "BfvParametersBuilder", "Ciphertext", "KeySwitchingKey", "RelinearizationKey",
+           "GaloisKey", "EvaluationKey", "Multiplicator", "FheError", "NTT", "POWER_BASIS"]
+
+
+def _ptr(a: np.ndarray) -> int:
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+class BfvParameters:
+    """fhe::bfv::BfvParameters (bfv/parameters.rs:88-114), built by
+    BfvParametersBuilder::build (:560-738).  `device=-1` builds the host tables only."""
+
+    def __init__(self, degree: int, plaintext_modulus: int, moduli: Optional[Sequence[int]] = None,
+                 moduli_sizes: Optional[Sequence[int]] = None, psi: Optional[Sequence[int]] = None,
+                 device: int = 0):
+        L = _capi.lib()
+        if (moduli is None) == (moduli_sizes is None):
+            # parameters.rs:455-466
+            raise FheError(_capi.INVALID_ARGUMENT, "exactly one of moduli / moduli_sizes must be given")
+        pt = int(plaintext_modulus)
+        if pt <= 0:
+            raise FheError(_capi.INVALID_ARGUMENT, "plaintext modulus must be positive")
+        pt_bytes = pt.to_bytes(max(1, (pt.bit_length() + 7) // 8), "little")
+        buf = (C.c_uint8 * len(pt_bytes)).from_buffer_copy(pt_bytes)
+        h = C.c_void_p()
+        if moduli is not None:
+            m = np.ascontiguousarray(np.array([int(x) for x in moduli], dtype=np.uint64))
+            ps = None
+            if psi is not None:
+                ps = np.ascontiguousarray(np.array([int(x) for x in psi], dtype=np.uint64))
+                if len(ps) != 2 * len(m) + 1:
+                    raise FheError(_capi.INVALID_ARGUMENT, "psi needs one root per modulus and extension prime")
+            check(L.fhe_b200_params_create(device, degree, _ptr(m), len(m), C.addressof(buf), len(pt_bytes),
+                                           _ptr(ps) if ps is not None else None, C.byref(h)))
+        else:
+            if psi is not None:
+                raise FheError(_capi.INVALID_ARGUMENT, "psi requires explicit moduli")
+            s = np.ascontiguousarray(np.array(list(moduli_sizes), dtype=np.uint32))
+            check(L.fhe_b200_params_create_from_sizes(device, degree, s.ctypes.data, len(s), C.addressof(buf),
+                                                      len(pt_bytes), C.byref(h)))
+        self._h = h
+        self.device = device
+        self._plaintext = pt
+        self._degree = L.fhe_b200_params_degree(h)
+        n = L.fhe_b200_params_n_moduli(h)
+        out = np.zeros(n, np.uint64)
+        check(L.fhe_b200_params_moduli(h, _ptr(out)))
+        self._moduli = [int(x) for x in out]
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _capi.lib().fhe_b200_params_destroy(h)
+
+    def degree(self) -> int:  # parameters.rs:130
+        return self._degree
+
+    def moduli(self):  # parameters.rs:136
+        return list(self._moduli)
+
+    def plaintext(self) -> int:
+        return self._plaintext
+
+    def max_level(self) -> int:  # parameters.rs:173
+        return len(self._moduli) - 1
+
+    def mul_basis(self, level: int = 0):
+        """level moduli followed by the extension primes (parameters.rs:660-700)."""
+        L = _capi.lib()
+        n = C.c_uint32()
+        check(L.fhe_b200_params_mul_basis(self._h, level, None, C.byref(n)))
+        out = np.zeros(n.value, np.uint64)
+        check(L.fhe_b200_params_mul_basis(self._h, level, _ptr(out), C.byref(n)))
+        return [int(x) for x in out]
+
+    def psi(self, q: int) -> int:
+        r = C.c_uint64()
+        check(_capi.lib().fhe_b200_params_psi(self._h, q, C.byref(r)))
+        return r.value
+
+    def scaler_tables(self, level: int, which: int) -> Dict[str, object]:
+        """Host precompute inspection: RnsScaler tables (rns/scaler.rs:52-73)."""
+        L = _capi.lib()
+        nf, nt, sh = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(L.fhe_b200_debug_scaler_tables(self._h, level, which, C.byref(nf), C.byref(nt), C.byref(sh),
+                                             *([None] * 8)))
+        f, t = nf.value, nt.value
+        gamma, omega, tg = np.zeros(t, np.uint64), np.zeros((t, f), np.uint64), np.zeros(3, np.uint64)
+        tol, toh, tos = np.zeros(f, np.uint64), np.zeros(f, np.uint64), np.zeros(f, np.uint8)
+        tgl, tgh = np.zeros(f, np.uint64), np.zeros(f, np.uint64)
+        check(L.fhe_b200_debug_scaler_tables(self._h, level, which, C.byref(nf), C.byref(nt), C.byref(sh),
+                                             _ptr(gamma), _ptr(omega), _ptr(tg), _ptr(tol), _ptr(toh), _ptr(tos),
+                                             _ptr(tgl), _ptr(tgh)))
+        return dict(n_from=f, n_to=t, shift=sh.value, gamma=gamma, omega=omega, theta_gamma=tg,
+                    theta_omega_lo=tol, theta_omega_hi=toh, theta_omega_sign=tos,
+                    theta_garner_lo=tgl, theta_garner_hi=tgh)
+
+    def ntt_tables(self, q: int) -> Dict[str, object]:
+        n = self._degree
+        om, oms, zi, zis = (np.zeros(n, np.uint64) for _ in range(4))
+        ninv = C.c_uint64()
+        check(_capi.lib().fhe_b200_debug_ntt_tables(self._h, q, _ptr(om), _ptr(oms), _ptr(zi), _ptr(zis),
+                                                    C.byref(ninv)))
+        return dict(omegas=om, omegas_shoup=oms, zetas_inv=zi, zetas_inv_shoup=zis, size_inv=ninv.value)
+
+
+class BfvParametersBuilder:
+    """fhe::bfv::BfvParametersBuilder (bfv/parameters.rs:319-388)."""
+
+    def __init__(self):
+        self._degree = 0
+        self._plaintext = 0
+        self._moduli = None
+        self._sizes = None
+        self._psi = None
+
+    def set_degree(self, degree: int):
+        self._degree = degree
+        return self
+
+    def set_plaintext_modulus(self, t: int):
+        self._plaintext = t
+        return self
+
+    def set_moduli(self, moduli: Sequence[int]):
+        self._moduli = list(moduli)
+        return self
+
+    def set_moduli_sizes(self, sizes: Sequence[int]):
+        self._sizes = list(sizes)
+        return self
+
+    def set_ntt_roots(self, psi: Sequence[int]):
+        """2N-th roots per [moduli..., extension primes...] (the reference's own, for interchange)."""
+        self._psi = list(psi)
+        return self
+
+    def build(self, device: int = 0) -> BfvParameters:
+        return BfvParameters(self._degree, self._plaintext, self._moduli, self._sizes, self._psi, device)
+
+    build_arc = build
+
+
+class Ciphertext:
+    """A device-resident batch of fhe::bfv::Ciphertext (bfv/ciphertext.rs:18-32): `count`
+    ciphertexts of `parts` polynomials at `level`, words [count][parts][limbs][N]."""
+
+    def __init__(self, par: BfvParameters, count: int, parts: int = 2, level: int = 0, repr: int = NTT,
+                 stream: int = 0, mul_basis: bool = False):
+        h = C.c_void_p()
+        f = _capi.lib().fhe_b200_batch_alloc_mul_basis if mul_basis else _capi.lib().fhe_b200_batch_alloc
+        check(f(par._h, count, parts, level, repr, C.byref(h)))
+        self._h, self.par, self.stream = h, par, stream
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _capi.lib().fhe_b200_batch_free(h)
+
+    # -- shape
+    def _info(self):
+        c, p, lv, lm, r = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_int()
+        check(_capi.lib().fhe_b200_batch_info(self._h, C.byref(c), C.byref(p), C.byref(lv), C.byref(lm), C.byref(r)))
+        return c.value, p.value, lv.value, lm.value, r.value
+
+    @property
+    def count(self):
+        return self._info()[0]
+
+    def __len__(self):  # Ciphertext::len -> number of polynomials (ciphertext.rs:118)
+        return self._info()[1]
+
+    @property
+    def level(self):
+        return self._info()[2]
+
+    @property
+    def limbs(self):
+        return self._info()[3]
+
+    @property
+    def representation(self):
+        return self._info()[4]
+
+    def shape(self):
+        c, p, _, lm, _ = self._info()
+        return (c, p, lm, self.par.degree())
+
+    # -- transfer
+    @staticmethod
+    def from_host(par: BfvParameters, words: np.ndarray, level: int = 0, repr: int = NTT, stream: int = 0,
+                  mul_basis: bool = False) -> "Ciphertext":
+        """words: u64 [count][parts][limbs][N] as Vec<u64>::from(&Poly) (rq/convert.rs:474-503)."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        if words.ndim != 4 or words.shape[3] != par.degree():
+            raise FheError(_capi.INVALID_ARGUMENT, "expected [count][parts][limbs][N] words")
+        ct = Ciphertext(par, words.shape[0], words.shape[1], level, repr, stream, mul_basis)
+        if ct.limbs != words.shape[2]:
+            raise FheError(_capi.CONTEXT_MISMATCH, "limb count does not match the level")
+        check(_capi.lib().fhe_b200_batch_upload(ct._h, 0, words.shape[0], _ptr(words), stream))
+        check(_capi.lib().fhe_b200_sync(stream))
+        return ct
+
+    def upload(self, words: np.ndarray, first: int = 0):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        check(_capi.lib().fhe_b200_batch_upload(self._h, first, words.shape[0], _ptr(words), self.stream))
+
+    def to_host(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.shape(), np.uint64)
+        check(_capi.lib().fhe_b200_batch_download(self._h, 0, out.shape[0], _ptr(out), self.stream))
+        return out
+
+    def device_ptr(self) -> int:
+        p, n = C.c_void_p(), C.c_size_t()
+        check(_capi.lib().fhe_b200_batch_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value
+
+    def sync(self):
+        check(_capi.lib().fhe_b200_sync(self.stream))
+
+    def _like(self, parts: Optional[int] = None, level: Optional[int] = None) -> "Ciphertext":
+        c, p, lv, _, r = self._info()
+        return Ciphertext(self.par, c, parts or p, lv if level is None else level, r, self.stream)
+
+    def clone(self) -> "Ciphertext":
+        out = self._like()
+        check(_capi.lib().fhe_b200_batch_copy(out._h, self._h, self.stream))
+        return out
+
+    # -- representation (Poly::into_ntt / into_power_basis, rq/mod.rs:535, :590)
+    def into_ntt(self) -> "Ciphertext":
+        check(_capi.lib().fhe_b200_ntt_forward(self._h, self.stream))
+        return self
+
+    def into_power_basis(self) -> "Ciphertext":
+        check(_capi.lib().fhe_b200_ntt_backward(self._h, self.stream))
+        return self
+
+    # -- operators (bfv/ops/mod.rs:15-358)
+    def __iadd__(self, rhs: "Ciphertext"):
+        check(_capi.lib().fhe_b200_add(self._h, rhs._h, self.stream))
+        return self
+
+    def __isub__(self, rhs: "Ciphertext"):
+        check(_capi.lib().fhe_b200_sub(self._h, rhs._h, self.stream))
+        return self
+
+    def __add__(self, rhs: "Ciphertext") -> "Ciphertext":
+        out = self.clone()
+        out += rhs
+        return out
+
+    def __sub__(self, rhs: "Ciphertext") -> "Ciphertext":
+        out = self.clone()
+        out -= rhs
+        return out
+
+    def __neg__(self) -> "Ciphertext":
+        out = self.clone()
+        check(_capi.lib().fhe_b200_neg(out._h, out.stream))
+        return out
+
+    def __mul__(self, rhs: "Ciphertext") -> "Ciphertext":
+        """&Ciphertext * &Ciphertext -> 3-part ciphertext, no relinearization (ops/mod.rs:259-358)."""
+        out = self._like(parts=3)
+        check(_capi.lib().fhe_b200_mul(self._h, rhs._h, out._h, self.stream))
+        return out
+
+    def switch_down(self) -> "Ciphertext":
+        """Ciphertext::switch_down (ciphertext.rs:148-161), in place."""
+        check(_capi.lib().fhe_b200_switch_down(self._h, self.stream))
+        return self
+
+    def substitute(self, exponent: int) -> "Ciphertext":
+        """Poly::substitute on every polynomial (rq/mod.rs:360-389)."""
+        out = self._like()
+        check(_capi.lib().fhe_b200_substitute(self._h, exponent, out._h, self.stream))
+        return out
+
+    def scale(self, which: int) -> "Ciphertext":
+        """Poly::scale with the level's extender (0) / down scaler (1) (rq/mod.rs:669, rq/scaler.rs:55)."""
+        c, p, lv, _, r = self._info()
+        out = Ciphertext(self.par, c, p, lv, r, self.stream, mul_basis=(which == 0))
+        check(_capi.lib().fhe_b200_scale(self._h, which, out._h, self.stream))
+        return out
+
+
+class KeySwitchingKey:
+    """fhe::bfv::KeySwitchingKey (keys/key_switching_key.rs:22-45) from its NTT-domain words:
+    c0, c1 = [n_digits][ksk_limbs][N] (the `coefficients` of the Poly<NttShoup> elements)."""
+
+    def __init__(self, par: BfvParameters, c0: np.ndarray, c1: np.ndarray, ciphertext_level: int = 0,
+                 ksk_level: int = 0):
+        c0 = np.ascontiguousarray(c0, dtype=np.uint64)
+        c1 = np.ascontiguousarray(c1, dtype=np.uint64)
+        if c0.shape != c1.shape or c0.ndim != 3 or c0.shape[2] != par.degree():
+            raise FheError(_capi.INVALID_ARGUMENT, "expected c0, c1 as [digits][limbs][N]")
+        if c0.shape[1] != len(par.moduli()) - ksk_level:
+            raise FheError(_capi.CONTEXT_MISMATCH, "key limb count does not match ksk_level")
+        h = C.c_void_p()
+        check(_capi.lib().fhe_b200_ksk_upload(par._h, ciphertext_level, ksk_level, _ptr(c0), _ptr(c1),
+                                              c0.shape[0], C.byref(h)))
+        self._h, self.par = h, par
+        self.ciphertext_level, self.ksk_level = ciphertext_level, ksk_level
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _capi.lib().fhe_b200_ksk_free(h)
+
+    def key_switch(self, p: Ciphertext, part: int = 0) -> Ciphertext:
+        """KeySwitchingKey::key_switch (key_switching_key.rs:241-270) on polynomial `part` of a
+        POWER_BASIS batch; returns the (c0, c1) pair as a 2-part NTT batch at the key level."""
+        out = Ciphertext(self.par, p.count, 2, self.ksk_level, NTT, p.stream)
+        check(_capi.lib().fhe_b200_key_switch(p._h, part, self._h, out._h, p.stream))
+        return out
+
+
+class RelinearizationKey:
+    """fhe::bfv::RelinearizationKey (keys/relinearization_key.rs:23-26)."""
+
+    def __init__(self, ksk: KeySwitchingKey):
+        self.ksk = ksk
+
+    @staticmethod
+    def from_arrays(par: BfvParameters, c0, c1, ciphertext_level: int = 0, key_level: int = 0):
+        return RelinearizationKey(KeySwitchingKey(par, c0, c1, ciphertext_level, key_level))
+
+    def relinearizes(self, ct: Ciphertext) -> Ciphertext:
+        """RelinearizationKey::relinearizes (relinearization_key.rs:70-103): (c0,c1,c2) -> (c0,c1).
+        (The reference mutates `ct`; a device batch changes shape, so the result is returned.)"""
+        out = ct._like(parts=2)
+        check(_capi.lib().fhe_b200_relinearize(ct._h, self.ksk._h, out._h, ct.stream))
+        return out
+
+
+class GaloisKey:
+    """fhe::bfv::GaloisKey (keys/galois_key.rs:18-22)."""
+
+    def __init__(self, exponent: int, ksk: KeySwitchingKey):
+        self.exponent, self.ksk = exponent, ksk
+
+    @staticmethod
+    def from_arrays(par: BfvParameters, exponent: int, c0, c1, ciphertext_level: int = 0, key_level: int = 0):
+        return GaloisKey(exponent, KeySwitchingKey(par, c0, c1, ciphertext_level, key_level))
+
+    def relinearize(self, ct: Ciphertext) -> Ciphertext:
+        """GaloisKey::relinearize (galois_key.rs:63-86)."""
+        out = ct._like()
+        check(_capi.lib().fhe_b200_galois(ct._h, self.exponent, self.ksk._h, out._h, ct.stream))
+        return out
+
+
+class EvaluationKey:
+    """The rotation subset of fhe::bfv::EvaluationKey (keys/evaluation_key.rs:110-170):
+    a map Galois exponent -> GaloisKey."""
+
+    def __init__(self, par: BfvParameters):
+        self.par = par
+        self.gk: Dict[int, GaloisKey] = {}
+
+    def add_galois_key(self, gk: GaloisKey):
+        self.gk[gk.exponent % (2 * self.par.degree())] = gk
+
+    def supports_row_rotation(self) -> bool:
+        return (2 * self.par.degree() - 1) in self.gk
+
+    def supports_column_rotation_by(self, i: int) -> bool:
+        return pow(3, i, 2 * self.par.degree()) in self.gk
+
+    def rotates_rows(self, ct: Ciphertext) -> Ciphertext:  # evaluation_key.rs:110-126
+        e = 2 * self.par.degree() - 1
+        if e not in self.gk:
+            raise FheError(_capi.INVALID_ARGUMENT, "EvaluationKeyError: row rotation not supported by this key")
+        return self.gk[e].relinearize(ct)
+
+    def rotates_columns_by(self, ct: Ciphertext, i: int) -> Ciphertext:  # evaluation_key.rs:145-170
+        e = pow(3, i, 2 * self.par.degree())  # :278-286
+        if e not in self.gk:
+            raise FheError(_capi.INVALID_ARGUMENT, "EvaluationKeyError: column rotation not supported by this key")
+        return self.gk[e].relinearize(ct)
+
+
+class Multiplicator:
+    """fhe::bfv::Multiplicator (bfv/ops/mul.rs:22-33) with the default strategy
+    (Multiplicator::default, mul.rs:101-138: extend by factor 1, scale by t/Q, relinearize)."""
+
+    def __init__(self, rk: RelinearizationKey):
+        self.rk = rk
+        self.par = rk.ksk.par
+        self.level = rk.ksk.ciphertext_level
+        self.mod_switch = False
+
+    @staticmethod
+    def default(rk: RelinearizationKey) -> "Multiplicator":
+        return Multiplicator(rk)
+
+    def enable_mod_switching(self):  # mul.rs:155-162
+        if self.level >= self.par.max_level():
+            raise FheError(_capi.NO_MORE_CONTEXT, "NoMoreContext")
+        self.mod_switch = True
+        return self
+
+    def multiply(self, lhs: Ciphertext, rhs: Ciphertext) -> Ciphertext:
+        """Multiplicator::multiply (mul.rs:165-243)."""
+        if lhs.level != self.level or rhs.level != self.level:
+            raise FheError(_capi.INVALID_LEVEL, "InvalidLevel")  # mul.rs:168-181
+        out = lhs._like(parts=2, level=self.level + (1 if self.mod_switch else 0))
+        check(_capi.lib().fhe_b200_mul_relin(lhs._h, rhs._h, self.rk.ksk._h, 1 if self.mod_switch else 0,
+                                             out._h, lhs.stream))
+        return out

@@ -1,0 +1,874 @@
+// C ABI of the engine (include/fhe_b200.h): parameter precompute + upload, device batches,
+// key material, and the batched homomorphic operations built from the kernels of
+// ntt.cu / kernels.cu.  No CPU fallback: compute entry points require a CUDA device.
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fhe_b200.h"
+#include "engine.hpp"
+#include "host/precompute.hpp"
+
+using namespace fhe_b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct ScalerData {
+  ScalerTablesH h;
+  ScalerDev dev;
+};
+
+struct LevelData {
+  u32 level = 0, L = 0, E = 0, K = 0;
+  RowIds ctx_ids, mul_ids;
+  std::vector<u64> mul_moduli;
+  ScalerData ext, down;
+  bool has_sd = false;
+  SwitchDownDev sd;
+};
+
+}  // namespace
+
+struct fhe_b200_params {
+  int device = -1;
+  u32 N = 0, logn = 0, Lmax = 0;
+  std::vector<u64> moduli, ext, primes, psi;
+  std::vector<u32> moduli_sizes;
+  BigUint t;
+  std::vector<NttTablesH> tables;  // host copies (kept for inspection / host-only handles)
+  std::vector<LimbDev> h_limbs;
+  LimbDev* d_limbs = nullptr;
+  std::vector<void*> d_allocs;
+  mutable std::mutex mu;
+  mutable std::map<u32, std::unique_ptr<LevelData>> levels;
+  mutable std::map<u32, int*> perms;
+
+  template <typename T>
+  T* to_dev(const std::vector<T>& v) const {
+    if (device < 0 || v.empty()) return nullptr;
+    T* d = nullptr;
+    FHE_CUDA(cudaMalloc(&d, v.size() * sizeof(T)));
+    const_cast<fhe_b200_params*>(this)->d_allocs.push_back(d);
+    FHE_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+  }
+  int prime_index(u64 q) const {
+    for (size_t i = 0; i < primes.size(); i++)
+      if (primes[i] == q) return (int)i;
+    return -1;
+  }
+  void upload_scaler(ScalerData& s, const std::vector<u64>& to_moduli) const {
+    ScalerDev& d = s.dev;
+    std::memset(&d, 0, sizeof(d));
+    d.n_from = s.h.n_from; d.n_to = s.h.n_to; d.is_one = s.h.is_one; d.shift = s.h.shift;
+    d.tg_lo = s.h.theta_gamma_lo; d.tg_hi = s.h.theta_gamma_hi; d.tg_sign = s.h.theta_gamma_sign;
+    for (size_t j = 0; j < to_moduli.size(); j++) d.to_ids[j] = (unsigned short)prime_index(to_moduli[j]);
+    d.gamma = to_dev(s.h.gamma);
+    d.omega = to_dev(s.h.omega);
+    d.to_lo = to_dev(s.h.theta_omega_lo);
+    d.to_hi = to_dev(s.h.theta_omega_hi);
+    d.to_sign = to_dev(s.h.theta_omega_sign);
+    d.tgar_lo = to_dev(s.h.theta_garner_lo);
+    d.tgar_hi = to_dev(s.h.theta_garner_hi);
+  }
+
+  // ContextLevel + MultiplicationParameters of one level (bfv/parameters.rs:600-700, :793-813)
+  const LevelData& level(u32 lv) const {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = levels.find(lv);
+    if (it != levels.end()) return *it->second;
+    if (lv >= Lmax) throw FheError(FHE_B200_INVALID_LEVEL, "InvalidLevel: level " + std::to_string(lv));
+    std::unique_ptr<LevelData> d(new LevelData());
+    d->level = lv;
+    d->L = Lmax - lv;
+    u32 bits = 0;
+    for (u32 i = 0; i < d->L; i++) bits += moduli_sizes[i];
+    d->E = (bits + 60 + 61) / 62;  // (modulus_size + 60).div_ceil(62), parameters.rs:689
+    d->K = d->L + d->E;
+    if (d->K > (u32)kMaxPos) throw FheError(FHE_B200_UNSUPPORTED, "too many limbs");
+    std::vector<u64> ctx(moduli.begin(), moduli.begin() + d->L);
+    d->mul_moduli = ctx;
+    d->mul_moduli.insert(d->mul_moduli.end(), ext.begin(), ext.begin() + d->E);
+    std::memset(&d->ctx_ids, 0, sizeof(RowIds));
+    std::memset(&d->mul_ids, 0, sizeof(RowIds));
+    d->ctx_ids.limbs_per_poly = d->L;
+    d->mul_ids.limbs_per_poly = d->K;
+    for (u32 i = 0; i < d->L; i++) d->ctx_ids.ids[i] = d->mul_ids.ids[i] = (unsigned short)i;
+    for (u32 j = 0; j < d->E; j++) d->mul_ids.ids[d->L + j] = (unsigned short)(Lmax + j);
+    RnsContextH from(ctx), to(d->mul_moduli);
+    d->ext.h = make_scaler_tables(from, to, BigUint(1), BigUint(1));
+    d->down.h = make_scaler_tables(to, from, t, from.product);
+    upload_scaler(d->ext, d->mul_moduli);
+    upload_scaler(d->down, ctx);
+    if (d->L >= 2) {  // rq/context.rs:65-71 and rq/mod.rs:444-468
+      d->has_sd = true;
+      u64 ql = ctx.back();
+      std::vector<u64> half_mod, inv, inv_s;
+      for (u32 i = 0; i + 1 < d->L; i++) {
+        u64 qi = ctx[i], iv;
+        if (!invmod_h(ql % qi, qi, &iv)) throw FheError(FHE_B200_INVALID_MODULUS, "NonCoprimeModuli");
+        half_mod.push_back(qi - (ql / 2) % qi);
+        inv.push_back(iv);
+        inv_s.push_back(ModulusH(qi).shoup(iv));
+      }
+      d->sd.q_last = ql;
+      d->sd.q_last_half = ql / 2;
+      d->sd.half_mod = to_dev(half_mod);
+      d->sd.inv = to_dev(inv);
+      d->sd.inv_s = to_dev(inv_s);
+    }
+    auto* raw = d.get();
+    levels[lv] = std::move(d);
+    return *raw;
+  }
+
+  // SubstitutionExponent::new (rq/mod.rs:99-121) folded with ctx.bitrev into one gather table:
+  // out[bitrev(j)] = in[bitrev((j*e + (e-1)/2) mod N)]
+  const int* perm(u32 exponent) const {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = perms.find(exponent);
+    if (it != perms.end()) return it->second;
+    std::vector<int> p(N);
+    auto brev = [&](u32 x) {
+      u32 r = 0;
+      for (u32 b = 0; b < logn; b++) r |= ((x >> b) & 1) << (logn - 1 - b);
+      return r;
+    };
+    u64 power = (exponent - 1) / 2;
+    for (u32 j = 0; j < N; j++) {
+      p[brev(j)] = (int)brev((u32)(power & (N - 1)));
+      power += exponent;
+    }
+    int* d = to_dev(p);
+    perms[exponent] = d;
+    return d;
+  }
+};
+
+struct fhe_b200_batch {
+  const fhe_b200_params* par;
+  u32 count, parts, level, limbs;
+  int repr;
+  bool mul_basis;
+  u64* d;
+  size_t words_per_ct() const { return ((size_t)parts * limbs) << par->logn; }
+};
+
+struct fhe_b200_ksk {
+  const fhe_b200_params* par;
+  u32 ct_level, ksk_level, n_dig, Lk;
+  u64 *k0, *k1;
+};
+
+namespace {
+
+struct DeviceGuard {
+  explicit DeviceGuard(const fhe_b200_params* p) {
+    if (p->device < 0) throw FheError(FHE_B200_NO_DEVICE, "parameter set was created without a CUDA device");
+    FHE_CUDA(cudaSetDevice(p->device));
+  }
+};
+
+// stream-ordered scratch memory
+struct Workspace {
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  explicit Workspace(cudaStream_t s) : st(s) {}
+  u64* words(size_t n) {
+    void* p = nullptr;
+    FHE_CUDA(cudaMallocAsync(&p, n * sizeof(u64), st));
+    ptrs.push_back(p);
+    return (u64*)p;
+  }
+  ~Workspace() {
+    for (void* p : ptrs) cudaFreeAsync(p, st);
+  }
+};
+
+u32 chunk_size() {
+  static u32 c = [] {
+    const char* e = getenv("FHE_B200_CHUNK");
+    int v = e ? atoi(e) : 32;
+    return (u32)(v < 1 ? 1 : v);
+  }();
+  return c;
+}
+
+void check_same(const fhe_b200_batch* a, const fhe_b200_batch* b) {
+  if (a->par != b->par) throw FheError(FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch: batches use different parameters");
+  if (a->level != b->level) throw FheError(FHE_B200_INVALID_LEVEL, "InvalidLevel: operands are at different levels");
+  if (a->mul_basis != b->mul_basis || a->limbs != b->limbs)
+    throw FheError(FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
+}
+void need_repr(const fhe_b200_batch* b, int repr) {
+  if (b->repr != repr) throw FheError(FHE_B200_INVALID_REPRESENTATION, "IncorrectRepresentation");
+}
+const RowIds& ids_of(const fhe_b200_batch* b) {
+  const LevelData& lv = b->par->level(b->level);
+  return b->mul_basis ? lv.mul_ids : lv.ctx_ids;
+}
+
+// KeySwitchingKey::key_switch core on a contiguous power-basis buffer c2 [cts][L][N]
+// (key_switching_key.rs:241-270): out0/out1 (+ optional bases), rows (ct, j) at (ct*out_ct_rows + j).
+void key_switch_core(const fhe_b200_params* par, const fhe_b200_ksk* k, const u64* c2, u32 cts, const u64* base0,
+                     const u64* base1, u64* out0, u64* out1, u32 out_ct_rows, Workspace& ws, cudaStream_t st) {
+  const LevelData& kl = par->level(k->ksk_level);
+  const u32 L = k->n_dig, Lk = k->Lk;
+  u64* inter = ws.words(((size_t)cts * L * Lk) << par->logn);
+  // digit broadcast + reduction modulo q_j on load (rq/mod.rs:563-586), then NTT of every (digit, limb) row
+  launch_ntt(c2, inter, cts * L * Lk, kl.ctx_ids, par->d_limbs, par->logn, false, Lk, true, st);
+  launch_ksmac(inter, k->k0, k->k1, base0, base1, out0, out1, cts, L, Lk, out_ct_rows, kl.ctx_ids, par->d_limbs,
+               par->logn, st);
+}
+
+// extend -> tensor -> scale down of bfv/ops/mul.rs:192-206 for `cts` ciphertext pairs.
+// a, b: [cts][2][L][N] NTT.  split == 0: out0 = [cts][3][L][N] power basis (all three parts);
+// split == 1: out0 = [cts][2][L][N] (c0, c1), out1 = [cts][L][N] (c2), all power basis.
+void mul_core(const fhe_b200_params* par, const LevelData& lv, const u64* a, const u64* b, u32 cts, u64* out0,
+              u64* out1, int split, Workspace& ws, cudaStream_t st) {
+  const u32 L = lv.L, E = lv.E, K = lv.K, logn = par->logn;
+  const size_t row = (size_t)1 << logn;
+  u64* A_l = ws.words((size_t)cts * 2 * L * row);
+  u64* A_r = ws.words((size_t)cts * 2 * L * row);
+  u64* X_l = ws.words((size_t)cts * 2 * E * row);
+  u64* X_r = ws.words((size_t)cts * 2 * E * row);
+  u64* T = ws.words((size_t)cts * 3 * K * row);
+  RowIds ext_ids;
+  std::memset(&ext_ids, 0, sizeof(ext_ids));
+  ext_ids.limbs_per_poly = E;
+  for (u32 j = 0; j < E; j++) ext_ids.ids[j] = lv.mul_ids.ids[L + j];
+  // rq/scaler.rs:69-79: backward NTT of the source rows
+  launch_ntt(a, A_l, cts * 2 * L, lv.ctx_ids, par->d_limbs, logn, true, 1, false, st);
+  launch_ntt(b, A_r, cts * 2 * L, lv.ctx_ids, par->d_limbs, logn, true, 1, false, st);
+  // rq/scaler.rs:85-94: exact base extension to the E new limbs (common prefix is kept as is, :61-65)
+  launch_scale(lv.ext.dev, par->d_limbs, A_l, X_l, nullptr, cts * 2, E, L, E, 0, logn, st);
+  launch_scale(lv.ext.dev, par->d_limbs, A_r, X_r, nullptr, cts * 2, E, L, E, 0, logn, st);
+  // rq/scaler.rs:97-115: forward NTT of the new rows
+  launch_ntt(X_l, X_l, cts * 2 * E, ext_ids, par->d_limbs, logn, false, 1, false, st);
+  launch_ntt(X_r, X_r, cts * 2 * E, ext_ids, par->d_limbs, logn, false, 1, false, st);
+  // mul.rs:198-201
+  launch_tensor(a, b, X_l, X_r, T, cts, L, E, lv.mul_ids, par->d_limbs, logn, st);
+  // mul.rs:204-206: scale down by t/Q (backward NTT of K rows, exact scaling K -> L)
+  launch_ntt(T, T, cts * 3 * K, lv.mul_ids, par->d_limbs, logn, true, 1, false, st);
+  launch_scale(lv.down.dev, par->d_limbs, T, out0, out1, cts * 3, L, 0, L, split, logn, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+#define API_BEGIN try {
+#define API_END                                                                   \
+  }                                                                               \
+  catch (const FheError& e) { g_last_error = e.what(); return e.code; }           \
+  catch (const CudaFail& f) {                                                     \
+    g_last_error = std::string(f.what) + ": " + cudaGetErrorString(f.err);        \
+    cudaGetLastError();                                                           \
+    return f.err == cudaErrorMemoryAllocation ? FHE_B200_OUT_OF_MEMORY : FHE_B200_CUDA_ERROR; \
+  }                                                                               \
+  catch (const std::bad_alloc&) { g_last_error = "host out of memory"; return FHE_B200_OUT_OF_MEMORY; } \
+  catch (const std::exception& e) { g_last_error = e.what(); return FHE_B200_INVALID_ARGUMENT; } \
+  return FHE_B200_OK;
+#define REQUIRE(c, code, msg) \
+  do { if (!(c)) throw FheError(code, msg); } while (0)
+
+const char* fhe_b200_version(void) { return "fhe_b200 0.1 (sm_100a)"; }
+const char* fhe_b200_last_error(void) { return g_last_error.c_str(); }
+uint64_t fhe_b200_launch_count(void) { return g_launches.load(); }
+
+static int params_build(int device, uint32_t degree, const std::vector<u64>& moduli, const uint8_t* pt,
+                        uint32_t pt_len, const uint64_t* psi, fhe_b200_params** out) {
+  API_BEGIN
+  REQUIRE(out && pt && pt_len, FHE_B200_INVALID_ARGUMENT, "null argument");
+  // BfvParametersBuilder::validate_configuration (parameters.rs:440-468)
+  REQUIRE(degree >= 8 && degree <= 65536 && (degree & (degree - 1)) == 0, FHE_B200_INVALID_DEGREE,
+          "InvalidPolynomialDegree: " + std::to_string(degree));
+  REQUIRE(!moduli.empty() && moduli.size() < 32, FHE_B200_INVALID_ARGUMENT, "MissingCiphertextModulusSpecification");
+  std::unique_ptr<fhe_b200_params> p(new fhe_b200_params());
+  p->device = device;
+  p->N = degree;
+  p->logn = (u32)__builtin_ctz(degree);
+  p->Lmax = (u32)moduli.size();
+  p->moduli = moduli;
+  p->t = BigUint::from_le_bytes(pt, pt_len);
+  REQUIRE(!p->t.is_zero(), FHE_B200_INVALID_ARGUMENT, "plaintext modulus is zero");
+  // validate_moduli (parameters.rs:471-552)
+  BigUint Q(1);
+  for (size_t i = 0; i < moduli.size(); i++) {
+    ModulusH m(moduli[i]);
+    for (size_t j = 0; j < i; j++) REQUIRE(moduli[j] != moduli[i], FHE_B200_INVALID_MODULUS, "DuplicateModuli");
+    REQUIRE(moduli[i] % (2 * (u64)degree) == 1 && is_prime_u64(moduli[i]), FHE_B200_NTT_UNAVAILABLE,
+            "CiphertextModulusNotNttFriendly: " + std::to_string(moduli[i]));
+    u64 tm = p->t.mod_u64(moduli[i]), dummy;
+    REQUIRE(tm != 0 && invmod_h(tm, moduli[i], &dummy), FHE_B200_INVALID_MODULUS, "PlaintextModulusNotCoprime");
+    p->moduli_sizes.push_back(64 - (u32)clz64(moduli[i]));
+    Q = Q * BigUint(moduli[i]);
+  }
+  REQUIRE(p->t < Q, FHE_B200_INVALID_ARGUMENT, "PlaintextModulusExceedsCiphertextModulus");
+  // extended basis (parameters.rs:660-676)
+  u64 ub = 1ull << 62;
+  while (p->ext.size() != moduli.size() + 1) {
+    REQUIRE(generate_prime(62, 2 * (u64)degree, ub, &ub), FHE_B200_INVALID_MODULUS, "NotEnoughPrimes");
+    bool dup = false;
+    for (u64 q : p->ext) dup |= q == ub;
+    for (u64 q : moduli) dup |= q == ub;
+    if (!dup) p->ext.push_back(ub);
+  }
+  p->primes = moduli;
+  p->primes.insert(p->primes.end(), p->ext.begin(), p->ext.end());
+  if (device >= 0) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
+      cudaGetLastError();
+      throw FheError(FHE_B200_NO_DEVICE, "CUDA device " + std::to_string(device) + " not available");
+    }
+    FHE_CUDA(cudaSetDevice(device));
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
+  for (size_t i = 0; i < p->primes.size(); i++) {
+    u64 q = p->primes[i];
+    u64 r = psi ? psi[i] : default_psi(q, degree);
+    p->psi.push_back(r);
+    p->tables.push_back(make_ntt_tables(q, degree, r));
+    const NttTablesH& t = p->tables.back();
+    ModulusH m(q);
+    LimbDev d;
+    std::memset(&d, 0, sizeof(d));
+    d.p = q; d.p2 = 2 * q; d.bhi = m.bhi; d.blo = m.blo; d.c128 = m.c128;
+    d.ninv = t.ninv; d.ninv_s = t.ninv_s; d.zn = t.zn; d.zn_s = t.zn_s;
+    d.om = p->to_dev(t.om); d.om_s = p->to_dev(t.om_s);
+    d.zi = p->to_dev(t.zi); d.zi_s = p->to_dev(t.zi_s);
+    p->h_limbs.push_back(d);
+  }
+  p->d_limbs = p->to_dev(p->h_limbs);
+  *out = p.release();
+  API_END
+}
+
+int fhe_b200_params_create(int device, uint32_t degree, const uint64_t* moduli, uint32_t n_moduli,
+                           const uint8_t* plaintext_le, uint32_t plaintext_len, const uint64_t* psi,
+                           fhe_b200_params** out) {
+  if (!moduli || !n_moduli) { g_last_error = "null moduli"; return FHE_B200_INVALID_ARGUMENT; }
+  std::vector<u64> m(moduli, moduli + n_moduli);
+  return params_build(device, degree, m, plaintext_le, plaintext_len, psi, out);
+}
+
+int fhe_b200_params_create_from_sizes(int device, uint32_t degree, const uint32_t* sizes, uint32_t n_moduli,
+                                      const uint8_t* plaintext_le, uint32_t plaintext_len, fhe_b200_params** out) {
+  if (!sizes || !n_moduli) { g_last_error = "null sizes"; return FHE_B200_INVALID_ARGUMENT; }
+  if (degree < 8 || (degree & (degree - 1))) { g_last_error = "InvalidPolynomialDegree"; return FHE_B200_INVALID_DEGREE; }
+  // BfvParametersBuilder::generate_moduli (parameters.rs:391-431)
+  std::vector<u64> m;
+  for (uint32_t i = 0; i < n_moduli; i++) {
+    if (sizes[i] > 62 || sizes[i] < 10) { g_last_error = "InvalidModulusSize"; return FHE_B200_INVALID_MODULUS; }
+    u64 ub = 1ull << sizes[i];
+    for (;;) {
+      u64 q;
+      if (!generate_prime((int)sizes[i], 2 * (u64)degree, ub, &q)) { g_last_error = "NotEnoughPrimes"; return FHE_B200_INVALID_MODULUS; }
+      bool dup = false;
+      for (u64 x : m) dup |= x == q;
+      if (!dup) { m.push_back(q); break; }
+      ub = q;
+    }
+  }
+  return params_build(device, degree, m, plaintext_le, plaintext_len, nullptr, out);
+}
+
+int fhe_b200_params_destroy(fhe_b200_params* p) {
+  if (!p) return FHE_B200_OK;
+  if (p->device >= 0) {
+    cudaSetDevice(p->device);
+    for (void* d : p->d_allocs) cudaFree(d);
+  }
+  delete p;
+  return FHE_B200_OK;
+}
+uint32_t fhe_b200_params_degree(const fhe_b200_params* p) { return p ? p->N : 0; }
+uint32_t fhe_b200_params_n_moduli(const fhe_b200_params* p) { return p ? p->Lmax : 0; }
+int fhe_b200_params_moduli(const fhe_b200_params* p, uint64_t* out) {
+  if (!p || !out) return FHE_B200_INVALID_ARGUMENT;
+  for (u32 i = 0; i < p->Lmax; i++) out[i] = p->moduli[i];
+  return FHE_B200_OK;
+}
+int fhe_b200_params_mul_basis(const fhe_b200_params* p, uint32_t level, uint64_t* out, uint32_t* n) {
+  API_BEGIN
+  REQUIRE(p && n, FHE_B200_INVALID_ARGUMENT, "null argument");
+  const LevelData& lv = p->level(level);
+  *n = lv.K;
+  if (out) for (u32 i = 0; i < lv.K; i++) out[i] = lv.mul_moduli[i];
+  API_END
+}
+int fhe_b200_params_psi(const fhe_b200_params* p, uint64_t q, uint64_t* psi) {
+  if (!p || !psi) return FHE_B200_INVALID_ARGUMENT;
+  int i = p->prime_index(q);
+  if (i < 0) { g_last_error = "prime not in parameter set"; return FHE_B200_INVALID_MODULUS; }
+  *psi = p->psi[i];
+  return FHE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------ batches
+static int batch_alloc(const fhe_b200_params* p, uint32_t count, uint32_t parts, uint32_t level, int repr,
+                       bool mul_basis, fhe_b200_batch** out) {
+  API_BEGIN
+  REQUIRE(p && out, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE(count > 0 && parts > 0, FHE_B200_INVALID_ARGUMENT, "empty batch");
+  REQUIRE(repr == FHE_B200_POWER_BASIS || repr == FHE_B200_NTT, FHE_B200_INVALID_REPRESENTATION, "bad representation");
+  DeviceGuard g(p);
+  const LevelData& lv = p->level(level);
+  std::unique_ptr<fhe_b200_batch> b(new fhe_b200_batch());
+  b->par = p; b->count = count; b->parts = parts; b->level = level; b->repr = repr;
+  b->mul_basis = mul_basis;
+  b->limbs = mul_basis ? lv.K : lv.L;
+  b->d = nullptr;
+  FHE_CUDA(cudaMalloc(&b->d, b->words_per_ct() * count * sizeof(u64)));
+  *out = b.release();
+  API_END
+}
+int fhe_b200_batch_alloc(const fhe_b200_params* p, uint32_t count, uint32_t parts, uint32_t level, int repr,
+                         fhe_b200_batch** out) {
+  return batch_alloc(p, count, parts, level, repr, false, out);
+}
+int fhe_b200_batch_alloc_mul_basis(const fhe_b200_params* p, uint32_t count, uint32_t parts, uint32_t level,
+                                   int repr, fhe_b200_batch** out) {
+  return batch_alloc(p, count, parts, level, repr, true, out);
+}
+int fhe_b200_batch_free(fhe_b200_batch* b) {
+  if (!b) return FHE_B200_OK;
+  if (b->par->device >= 0) cudaSetDevice(b->par->device);
+  cudaFree(b->d);
+  delete b;
+  return FHE_B200_OK;
+}
+int fhe_b200_batch_info(const fhe_b200_batch* b, uint32_t* count, uint32_t* parts, uint32_t* level, uint32_t* limbs,
+                        int* repr) {
+  if (!b) return FHE_B200_INVALID_ARGUMENT;
+  if (count) *count = b->count;
+  if (parts) *parts = b->parts;
+  if (level) *level = b->level;
+  if (limbs) *limbs = b->limbs;
+  if (repr) *repr = b->repr;
+  return FHE_B200_OK;
+}
+int fhe_b200_batch_upload(fhe_b200_batch* b, uint32_t first, uint32_t n, const uint64_t* host, void* stream) {
+  API_BEGIN
+  REQUIRE(b && host, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE((uint64_t)first + n <= b->count, FHE_B200_INVALID_ARGUMENT, "range exceeds batch");
+  DeviceGuard g(b->par);
+  size_t w = b->words_per_ct();
+  FHE_CUDA(cudaMemcpyAsync(b->d + w * first, host, w * n * sizeof(u64), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  API_END
+}
+int fhe_b200_batch_download(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint64_t* host, void* stream) {
+  API_BEGIN
+  REQUIRE(b && host, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE((uint64_t)first + n <= b->count, FHE_B200_INVALID_ARGUMENT, "range exceeds batch");
+  DeviceGuard g(b->par);
+  size_t w = b->words_per_ct();
+  FHE_CUDA(cudaMemcpyAsync(host, b->d + w * first, w * n * sizeof(u64), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  FHE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  API_END
+}
+int fhe_b200_batch_copy(fhe_b200_batch* dst, const fhe_b200_batch* src, void* stream) {
+  API_BEGIN
+  REQUIRE(dst && src, FHE_B200_INVALID_ARGUMENT, "null argument");
+  check_same(dst, src);
+  REQUIRE(dst->parts == src->parts && dst->count == src->count, FHE_B200_BAD_POLY_COUNT, "shapes differ");
+  DeviceGuard g(src->par);
+  FHE_CUDA(cudaMemcpyAsync(dst->d, src->d, src->words_per_ct() * src->count * sizeof(u64), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  dst->repr = src->repr;
+  API_END
+}
+int fhe_b200_batch_device_ptr(const fhe_b200_batch* b, uint64_t** dptr, size_t* n_words) {
+  if (!b || !dptr) return FHE_B200_INVALID_ARGUMENT;
+  *dptr = (uint64_t*)b->d;
+  if (n_words) *n_words = b->words_per_ct() * b->count;
+  return FHE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------ keys
+int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uint32_t ksk_level, const uint64_t* c0,
+                        const uint64_t* c1, uint32_t n_digits, fhe_b200_ksk** out) {
+  API_BEGIN
+  REQUIRE(p && c0 && c1 && out, FHE_B200_INVALID_ARGUMENT, "null argument");
+  DeviceGuard g(p);
+  const LevelData& cl = p->level(ciphertext_level);
+  const LevelData& kl = p->level(ksk_level);
+  REQUIRE(ksk_level <= ciphertext_level, FHE_B200_INVALID_LEVEL, "key level must not exceed the ciphertext level");
+  REQUIRE(kl.L >= 2, FHE_B200_UNSUPPORTED, "single-modulus key level uses digit decomposition (not accelerated)");
+  REQUIRE(n_digits == cl.L, FHE_B200_CONTEXT_MISMATCH, "n_digits must equal the ciphertext level's limb count");
+  std::unique_ptr<fhe_b200_ksk> k(new fhe_b200_ksk());
+  k->par = p; k->ct_level = ciphertext_level; k->ksk_level = ksk_level; k->n_dig = n_digits; k->Lk = kl.L;
+  size_t bytes = ((size_t)n_digits * kl.L << p->logn) * sizeof(u64);
+  k->k0 = k->k1 = nullptr;
+  FHE_CUDA(cudaMalloc(&k->k0, bytes));
+  FHE_CUDA(cudaMalloc(&k->k1, bytes));
+  FHE_CUDA(cudaMemcpy(k->k0, c0, bytes, cudaMemcpyHostToDevice));
+  FHE_CUDA(cudaMemcpy(k->k1, c1, bytes, cudaMemcpyHostToDevice));
+  *out = k.release();
+  API_END
+}
+int fhe_b200_ksk_free(fhe_b200_ksk* k) {
+  if (!k) return FHE_B200_OK;
+  if (k->par->device >= 0) cudaSetDevice(k->par->device);
+  cudaFree(k->k0);
+  cudaFree(k->k1);
+  delete k;
+  return FHE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------ primitives
+static int ntt_batch(fhe_b200_batch* b, bool inverse, void* stream) {
+  API_BEGIN
+  REQUIRE(b, FHE_B200_INVALID_ARGUMENT, "null argument");
+  need_repr(b, inverse ? FHE_B200_NTT : FHE_B200_POWER_BASIS);
+  DeviceGuard g(b->par);
+  launch_ntt(b->d, b->d, b->count * b->parts * b->limbs, ids_of(b), b->par->d_limbs, b->par->logn, inverse, 1, false,
+             (cudaStream_t)stream);
+  FHE_CUDA(cudaGetLastError());
+  b->repr = inverse ? FHE_B200_POWER_BASIS : FHE_B200_NTT;
+  API_END
+}
+int fhe_b200_ntt_forward(fhe_b200_batch* b, void* stream) { return ntt_batch(b, false, stream); }
+int fhe_b200_ntt_backward(fhe_b200_batch* b, void* stream) { return ntt_batch(b, true, stream); }
+
+static int ew(EwOp op, fhe_b200_batch* a, const fhe_b200_batch* b, void* stream) {
+  API_BEGIN
+  REQUIRE(a && (b || op == EW_NEG), FHE_B200_INVALID_ARGUMENT, "null argument");
+  if (b) {
+    check_same(a, b);
+    REQUIRE(a->parts == b->parts && a->count == b->count, FHE_B200_BAD_POLY_COUNT, "operand shapes differ");
+    REQUIRE(a->repr == b->repr, FHE_B200_INVALID_REPRESENTATION, "IncorrectRepresentation");
+  }
+  DeviceGuard g(a->par);
+  launch_ew(op, a->d, b ? b->d : nullptr, (size_t)a->count * a->parts * a->limbs, ids_of(a), a->par->d_limbs,
+            a->par->logn, (cudaStream_t)stream);
+  FHE_CUDA(cudaGetLastError());
+  API_END
+}
+int fhe_b200_add(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream) { return ew(EW_ADD, a, b, stream); }
+int fhe_b200_sub(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream) { return ew(EW_SUB, a, b, stream); }
+int fhe_b200_neg(fhe_b200_batch* a, void* stream) { return ew(EW_NEG, a, nullptr, stream); }
+
+int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batch* out3, void* stream) {
+  API_BEGIN
+  REQUIRE(a && b && out3, FHE_B200_INVALID_ARGUMENT, "null argument");
+  check_same(a, b);
+  check_same(a, out3);
+  REQUIRE(!a->mul_basis, FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
+  REQUIRE(a->parts == 2 && b->parts == 2 && out3->parts == 3, FHE_B200_BAD_POLY_COUNT,
+          "MultiplicationPolynomialCount: expected 2 x 2 -> 3");
+  REQUIRE(a->count == b->count && a->count == out3->count, FHE_B200_INVALID_ARGUMENT, "batch sizes differ");
+  need_repr(a, FHE_B200_NTT);
+  need_repr(b, FHE_B200_NTT);
+  DeviceGuard g(a->par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const fhe_b200_params* par = a->par;
+  const LevelData& lv = par->level(a->level);
+  const size_t row = (size_t)1 << par->logn;
+  for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
+    u32 n = std::min(chunk_size(), a->count - c0);
+    Workspace ws(st);
+    u64* o = out3->d + (size_t)c0 * 3 * lv.L * row;
+    mul_core(par, lv, a->d + (size_t)c0 * 2 * lv.L * row, b->d + (size_t)c0 * 2 * lv.L * row, n, o, nullptr, 0, ws, st);
+    // rq/scaler.rs:97-115 forward NTT of the scaled result
+    launch_ntt(o, o, n * 3 * lv.L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+  }
+  FHE_CUDA(cudaGetLastError());
+  out3->repr = FHE_B200_NTT;
+  API_END
+}
+
+static void check_ksk(const fhe_b200_ksk* k, const fhe_b200_params* par, u32 level) {
+  REQUIRE(k->par == par, FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch: key belongs to other parameters");
+  REQUIRE(k->ct_level == level, FHE_B200_INVALID_LEVEL, "InvalidLevel: key is for another ciphertext level");
+  REQUIRE(k->ksk_level == k->ct_level, FHE_B200_UNSUPPORTED,
+          "key level != ciphertext level (switch-down after key switch) is not accelerated yet");
+}
+
+int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_b200_batch* out2, void* stream) {
+  API_BEGIN
+  REQUIRE(ct3 && rk && out2, FHE_B200_INVALID_ARGUMENT, "null argument");
+  check_same(ct3, out2);
+  REQUIRE(!ct3->mul_basis, FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
+  REQUIRE(ct3->parts == 3 && out2->parts == 2, FHE_B200_BAD_POLY_COUNT, "InvalidPolynomialCount: expected 3 -> 2");
+  REQUIRE(ct3->count == out2->count, FHE_B200_INVALID_ARGUMENT, "batch sizes differ");
+  need_repr(ct3, FHE_B200_NTT);
+  check_ksk(rk, ct3->par, ct3->level);
+  DeviceGuard g(ct3->par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const fhe_b200_params* par = ct3->par;
+  const LevelData& lv = par->level(ct3->level);
+  const size_t row = (size_t)1 << par->logn, L = lv.L;
+  for (u32 c0 = 0; c0 < ct3->count; c0 += chunk_size()) {
+    u32 n = std::min(chunk_size(), ct3->count - c0);
+    Workspace ws(st);
+    const u64* src = ct3->d + (size_t)c0 * 3 * L * row;
+    u64* dst = out2->d + (size_t)c0 * 2 * L * row;
+    u64* c2 = ws.words((size_t)n * L * row);
+    FHE_CUDA(cudaMemcpy2DAsync(dst, 2 * L * row * 8, src, 3 * L * row * 8, 2 * L * row * 8, n, cudaMemcpyDeviceToDevice, st));
+    FHE_CUDA(cudaMemcpy2DAsync(c2, L * row * 8, src + 2 * L * row, 3 * L * row * 8, L * row * 8, n, cudaMemcpyDeviceToDevice, st));
+    // relinearization_key.rs:85: c2 -> power basis
+    launch_ntt(c2, c2, n * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
+    key_switch_core(par, rk, c2, n, dst, dst + L * row, dst, dst + L * row, 2 * (u32)L, ws, st);
+  }
+  FHE_CUDA(cudaGetLastError());
+  out2->repr = FHE_B200_NTT;
+  API_END
+}
+
+int fhe_b200_mul_relin(const fhe_b200_batch* a, const fhe_b200_batch* b, const fhe_b200_ksk* rk, int mod_switch,
+                       fhe_b200_batch* out2, void* stream) {
+  API_BEGIN
+  REQUIRE(a && b && rk && out2, FHE_B200_INVALID_ARGUMENT, "null argument");
+  check_same(a, b);
+  REQUIRE(a->par == out2->par, FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch");
+  REQUIRE(!a->mul_basis && !out2->mul_basis, FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
+  REQUIRE(a->parts == 2 && b->parts == 2 && out2->parts == 2, FHE_B200_BAD_POLY_COUNT,
+          "MultiplicationPolynomialCount: expected 2 x 2 -> 2");
+  REQUIRE(a->count == b->count && a->count == out2->count, FHE_B200_INVALID_ARGUMENT, "batch sizes differ");
+  need_repr(a, FHE_B200_NTT);
+  need_repr(b, FHE_B200_NTT);
+  check_ksk(rk, a->par, a->level);
+  const fhe_b200_params* par = a->par;
+  const LevelData& lv = par->level(a->level);
+  if (mod_switch) {
+    REQUIRE(lv.L >= 2, FHE_B200_NO_MORE_CONTEXT, "NoMoreContext");  // mul.rs:155-162
+    REQUIRE(out2->level == a->level + 1, FHE_B200_INVALID_LEVEL, "output batch must be one level down");
+  } else {
+    REQUIRE(out2->level == a->level, FHE_B200_INVALID_LEVEL, "output batch must be at the operand level");
+  }
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row = (size_t)1 << par->logn, L = lv.L;
+  for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
+    u32 n = std::min(chunk_size(), a->count - c0);
+    Workspace ws(st);
+    u64* o = mod_switch ? ws.words((size_t)n * 2 * L * row) : out2->d + (size_t)c0 * 2 * L * row;
+    u64* c2 = ws.words((size_t)n * L * row);
+    mul_core(par, lv, a->d + (size_t)c0 * 2 * L * row, b->d + (size_t)c0 * 2 * L * row, n, o, c2, 1, ws, st);
+    // c0, c1 back to NTT.  c2 stays in power basis: mul.rs:206 + :212 forward- then inverse-transform it,
+    // and backward(forward(x)) == x for reduced x (ntt/mod.rs:73-74), so skipping both is bit-exact.
+    launch_ntt(o, o, n * 2 * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+    key_switch_core(par, rk, c2, n, o, o + L * row, o, o + L * row, 2 * (u32)L, ws, st);
+    if (mod_switch) {  // Ciphertext::switch_down, ciphertext.rs:148-161
+      launch_ntt(o, o, n * 2 * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
+      u64* dst = out2->d + (size_t)c0 * 2 * (L - 1) * row;
+      launch_switch_down(lv.sd, o, dst, n * 2, (u32)L, lv.ctx_ids, par->d_limbs, par->logn, st);
+      const LevelData& nl = par->level(a->level + 1);
+      launch_ntt(dst, dst, n * 2 * (u32)(L - 1), nl.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+    }
+  }
+  FHE_CUDA(cudaGetLastError());
+  out2->repr = FHE_B200_NTT;
+  API_END
+}
+
+int fhe_b200_substitute(const fhe_b200_batch* in, uint32_t exponent, fhe_b200_batch* out, void* stream) {
+  API_BEGIN
+  REQUIRE(in && out && in != out, FHE_B200_INVALID_ARGUMENT, "null or aliased argument");
+  check_same(in, out);
+  REQUIRE(in->parts == out->parts && in->count == out->count, FHE_B200_BAD_POLY_COUNT, "shapes differ");
+  need_repr(in, FHE_B200_NTT);
+  const fhe_b200_params* par = in->par;
+  exponent %= 2 * par->N;
+  REQUIRE(exponent & 1, FHE_B200_INVALID_EXPONENT, "InvalidSubstitutionExponent");
+  DeviceGuard g(par);
+  launch_gather(in->d, out->d, (size_t)in->count * in->parts * in->limbs, par->perm(exponent), par->logn,
+                (cudaStream_t)stream);
+  FHE_CUDA(cudaGetLastError());
+  out->repr = FHE_B200_NTT;
+  API_END
+}
+
+int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_ksk* gk, fhe_b200_batch* out,
+                    void* stream) {
+  API_BEGIN
+  REQUIRE(ct && gk && out && ct != out, FHE_B200_INVALID_ARGUMENT, "null or aliased argument");
+  check_same(ct, out);
+  REQUIRE(!ct->mul_basis, FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
+  REQUIRE(ct->parts == 2 && out->parts == 2, FHE_B200_BAD_POLY_COUNT, "InvalidPolynomialCount: expected 2");
+  REQUIRE(ct->count == out->count, FHE_B200_INVALID_ARGUMENT, "batch sizes differ");
+  need_repr(ct, FHE_B200_NTT);
+  check_ksk(gk, ct->par, ct->level);
+  const fhe_b200_params* par = ct->par;
+  exponent %= 2 * par->N;
+  REQUIRE(exponent & 1, FHE_B200_INVALID_EXPONENT, "InvalidSubstitutionExponent");
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const LevelData& lv = par->level(ct->level);
+  const size_t row = (size_t)1 << par->logn, L = lv.L;
+  const int* perm = par->perm(exponent);
+  for (u32 c0 = 0; c0 < ct->count; c0 += chunk_size()) {
+    u32 n = std::min(chunk_size(), ct->count - c0);
+    Workspace ws(st);
+    const u64* src = ct->d + (size_t)c0 * 2 * L * row;
+    u64* dst = out->d + (size_t)c0 * 2 * L * row;
+    u64* s = ws.words((size_t)n * 2 * L * row);
+    u64* c2 = ws.words((size_t)n * L * row);
+    // galois_key.rs:66: substitute both parts; part 1 becomes the key-switch input
+    launch_gather(src, s, (size_t)n * 2 * L, perm, par->logn, st);
+    FHE_CUDA(cudaMemcpy2DAsync(c2, L * row * 8, s + L * row, 2 * L * row * 8, L * row * 8, n, cudaMemcpyDeviceToDevice, st));
+    launch_ntt(c2, c2, n * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
+    // galois_key.rs:67 + :78: out0 = key_switch0 + substitute(ct[0]); out1 = key_switch1
+    key_switch_core(par, gk, c2, n, s, nullptr, dst, dst + L * row, 2 * (u32)L, ws, st);
+  }
+  FHE_CUDA(cudaGetLastError());
+  out->repr = FHE_B200_NTT;
+  API_END
+}
+
+int fhe_b200_key_switch(const fhe_b200_batch* pb, uint32_t part, const fhe_b200_ksk* k, fhe_b200_batch* out2,
+                        void* stream) {
+  API_BEGIN
+  REQUIRE(pb && k && out2, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE(pb->par == out2->par && pb->par == k->par, FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch");
+  REQUIRE(!pb->mul_basis && !out2->mul_basis, FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
+  REQUIRE(part < pb->parts && out2->parts == 2, FHE_B200_BAD_POLY_COUNT, "bad part index / output parts");
+  REQUIRE(pb->level == k->ct_level && out2->level == k->ksk_level, FHE_B200_INVALID_LEVEL, "InvalidLevel");
+  REQUIRE(pb->count == out2->count, FHE_B200_INVALID_ARGUMENT, "batch sizes differ");
+  need_repr(pb, FHE_B200_POWER_BASIS);
+  const fhe_b200_params* par = pb->par;
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row = (size_t)1 << par->logn, L = pb->limbs, Lk = k->Lk;
+  for (u32 c0 = 0; c0 < pb->count; c0 += chunk_size()) {
+    u32 n = std::min(chunk_size(), pb->count - c0);
+    Workspace ws(st);
+    u64* c2 = ws.words((size_t)n * L * row);
+    FHE_CUDA(cudaMemcpy2DAsync(c2, L * row * 8, pb->d + ((size_t)c0 * pb->parts + part) * L * row,
+                               pb->parts * L * row * 8, L * row * 8, n, cudaMemcpyDeviceToDevice, st));
+    u64* dst = out2->d + (size_t)c0 * 2 * Lk * row;
+    key_switch_core(par, k, c2, n, nullptr, nullptr, dst, dst + Lk * row, 2 * (u32)Lk, ws, st);
+  }
+  FHE_CUDA(cudaGetLastError());
+  out2->repr = FHE_B200_NTT;
+  API_END
+}
+
+int fhe_b200_switch_down(fhe_b200_batch* b, void* stream) {
+  API_BEGIN
+  REQUIRE(b, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE(!b->mul_basis, FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
+  need_repr(b, FHE_B200_NTT);
+  const fhe_b200_params* par = b->par;
+  const LevelData& lv = par->level(b->level);
+  REQUIRE(lv.L >= 2, FHE_B200_NO_MORE_CONTEXT, "NoMoreContext");
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const LevelData& nl = par->level(b->level + 1);
+  const u32 polys = b->count * b->parts;
+  u64* nd = nullptr;
+  FHE_CUDA(cudaMalloc(&nd, ((size_t)polys * nl.L << par->logn) * sizeof(u64)));
+  launch_ntt(b->d, b->d, polys * lv.L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
+  launch_switch_down(lv.sd, b->d, nd, polys, lv.L, lv.ctx_ids, par->d_limbs, par->logn, st);
+  launch_ntt(nd, nd, polys * nl.L, nl.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+  FHE_CUDA(cudaGetLastError());
+  FHE_CUDA(cudaStreamSynchronize(st));
+  cudaFree(b->d);
+  b->d = nd;
+  b->level += 1;
+  b->limbs = nl.L;
+  API_END
+}
+
+int fhe_b200_scale(const fhe_b200_batch* in, int which, fhe_b200_batch* out, void* stream) {
+  API_BEGIN
+  REQUIRE(in && out && in != out, FHE_B200_INVALID_ARGUMENT, "null or aliased argument");
+  REQUIRE(in->par == out->par, FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch");
+  REQUIRE(in->level == out->level, FHE_B200_INVALID_LEVEL, "InvalidLevel");
+  REQUIRE(in->count == out->count && in->parts == out->parts, FHE_B200_BAD_POLY_COUNT, "shapes differ");
+  REQUIRE(which == 0 || which == 1, FHE_B200_INVALID_ARGUMENT, "which must be 0 or 1");
+  REQUIRE(in->mul_basis == (which == 1) && out->mul_basis == (which == 0), FHE_B200_CONTEXT_MISMATCH,
+          "PolynomialContextMismatch");
+  need_repr(in, FHE_B200_NTT);
+  const fhe_b200_params* par = in->par;
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const LevelData& lv = par->level(in->level);
+  const size_t row = (size_t)1 << par->logn;
+  const u32 polys = in->count * in->parts;
+  Workspace ws(st);
+  u64* pb = ws.words((size_t)polys * in->limbs * row);
+  launch_ntt(in->d, pb, polys * in->limbs, ids_of(in), par->d_limbs, par->logn, true, 1, false, st);
+  if (which == 0) {  // extender: common prefix copied, E new rows computed (rq/scaler.rs:61-65, :85-115)
+    FHE_CUDA(cudaMemcpy2DAsync(out->d, lv.K * row * 8, in->d, lv.L * row * 8, lv.L * row * 8, polys,
+                               cudaMemcpyDeviceToDevice, st));
+    u64* x = ws.words((size_t)polys * lv.E * row);
+    launch_scale(lv.ext.dev, par->d_limbs, pb, x, nullptr, polys, lv.E, lv.L, lv.E, 0, par->logn, st);
+    RowIds ext_ids;
+    std::memset(&ext_ids, 0, sizeof(ext_ids));
+    ext_ids.limbs_per_poly = lv.E;
+    for (u32 j = 0; j < lv.E; j++) ext_ids.ids[j] = lv.mul_ids.ids[lv.L + j];
+    launch_ntt(x, x, polys * lv.E, ext_ids, par->d_limbs, par->logn, false, 1, false, st);
+    FHE_CUDA(cudaMemcpy2DAsync(out->d + lv.L * row, lv.K * row * 8, x, lv.E * row * 8, lv.E * row * 8, polys,
+                               cudaMemcpyDeviceToDevice, st));
+  } else {
+    launch_scale(lv.down.dev, par->d_limbs, pb, out->d, nullptr, polys, lv.L, 0, lv.L, 0, par->logn, st);
+    launch_ntt(out->d, out->d, polys * lv.L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+  }
+  FHE_CUDA(cudaGetLastError());
+  out->repr = FHE_B200_NTT;
+  API_END
+}
+
+int fhe_b200_sync(void* stream) {
+  API_BEGIN
+  FHE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  API_END
+}
+
+// ------------------------------------------------------------------------------ inspection
+int fhe_b200_debug_scaler_tables(const fhe_b200_params* p, uint32_t level, int which, uint32_t* n_from, uint32_t* n_to,
+                                 uint32_t* shift, uint64_t* gamma, uint64_t* omega, uint64_t* theta_gamma,
+                                 uint64_t* theta_omega_lo, uint64_t* theta_omega_hi, uint8_t* theta_omega_sign,
+                                 uint64_t* theta_garner_lo, uint64_t* theta_garner_hi) {
+  API_BEGIN
+  REQUIRE(p, FHE_B200_INVALID_ARGUMENT, "null argument");
+  const LevelData& lv = p->level(level);
+  const ScalerTablesH& h = which ? lv.down.h : lv.ext.h;
+  if (n_from) *n_from = h.n_from;
+  if (n_to) *n_to = h.n_to;
+  if (shift) *shift = h.shift;
+  auto cp = [](uint64_t* dst, const std::vector<u64>& v) {
+    if (dst) for (size_t i = 0; i < v.size(); i++) dst[i] = v[i];
+  };
+  cp(gamma, h.gamma);
+  cp(omega, h.omega);
+  if (theta_gamma) { theta_gamma[0] = h.theta_gamma_lo; theta_gamma[1] = h.theta_gamma_hi; theta_gamma[2] = h.theta_gamma_sign; }
+  cp(theta_omega_lo, h.theta_omega_lo);
+  cp(theta_omega_hi, h.theta_omega_hi);
+  if (theta_omega_sign) for (size_t i = 0; i < h.theta_omega_sign.size(); i++) theta_omega_sign[i] = h.theta_omega_sign[i];
+  cp(theta_garner_lo, h.theta_garner_lo);
+  cp(theta_garner_hi, h.theta_garner_hi);
+  API_END
+}
+
+int fhe_b200_debug_ntt_tables(const fhe_b200_params* p, uint64_t q, uint64_t* omegas, uint64_t* omegas_shoup,
+                              uint64_t* zetas_inv, uint64_t* zetas_inv_shoup, uint64_t* size_inv) {
+  API_BEGIN
+  REQUIRE(p, FHE_B200_INVALID_ARGUMENT, "null argument");
+  int i = p->prime_index(q);
+  REQUIRE(i >= 0, FHE_B200_INVALID_MODULUS, "prime not in parameter set");
+  const NttTablesH& t = p->tables[i];
+  auto cp = [](uint64_t* dst, const std::vector<u64>& v) {
+    if (dst) for (size_t k = 0; k < v.size(); k++) dst[k] = v[k];
+  };
+  cp(omegas, t.om);
+  cp(omegas_shoup, t.om_s);
+  cp(zetas_inv, t.zi);
+  cp(zetas_inv_shoup, t.zi_s);
+  if (size_inv) *size_inv = t.ninv;
+  API_END
+}
+
+}  // extern "C"

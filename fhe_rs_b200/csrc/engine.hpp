@@ -1,0 +1,85 @@
+// Internal launch interfaces shared by ntt.cu / kernels.cu / capi.cu.
+#pragma once
+#include <atomic>
+#include <cuda_runtime.h>
+
+#include "ntt.cuh"
+
+namespace fhe_b200 {
+
+extern std::atomic<unsigned long long> g_launches;
+
+struct CudaFail {
+  cudaError_t err;
+  const char* what;
+};
+#define FHE_CUDA(x)                                         \
+  do {                                                      \
+    cudaError_t e__ = (x);                                  \
+    if (e__ != cudaSuccess) throw CudaFail{e__, #x};        \
+  } while (0)
+
+// position -> limb id map of the rows of a buffer
+struct RowIds {
+  u32 limbs_per_poly;
+  unsigned short ids[kMaxPos];
+};
+
+// ---- NTT (ntt.cu)
+// Transforms n_rows rows of N words.  in may differ from out (first pass reads in).
+// in_div / reduce_on_load: see NttArgs.
+void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
+                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st);
+
+// ---- element-wise (kernels.cu)
+enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2 };
+void launch_ew(EwOp op, u64* a, const u64* b, size_t n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
+               cudaStream_t st);
+
+// tensor product of two 2-part ciphertexts over the multiplication basis (mul.rs:198-201).
+// a,b: [ct][2][L][N] (common-prefix limbs, NTT); xa,xb: [ct][2][E][N] (extension limbs, NTT);
+// out: [ct][3][K][N].
+void launch_tensor(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 E,
+                   const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st);
+
+// exact RNS scaler (rns/scaler.rs:249-352), tables resident on the device
+struct ScalerDev {
+  u32 n_from, n_to, is_one, shift;
+  u64 tg_lo, tg_hi;
+  u32 tg_sign, pad;
+  const u64* gamma;       // [n_to]
+  const u64* omega;       // [n_to][n_from]
+  const u64* to_lo;       // theta_omega [n_from]
+  const u64* to_hi;
+  const unsigned char* to_sign;
+  const u64* tgar_lo;     // theta_garner [n_from]
+  const u64* tgar_hi;
+  unsigned short to_ids[kMaxPos];
+};
+// in: [polys][n_from][N] power basis.  Output rows `start .. start+n_out` of the `to` basis:
+//  split3 == 0: out0 + (poly * out_rows_per_poly + row) * N
+//  split3 == 1: polys come in triples (c0,c1,c2); c0,c1 -> out0 as [ct][2][n_out][N], c2 -> out1 as [ct][n_out][N]
+void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* out0, u64* out1, u32 polys,
+                  u32 out_rows_per_poly, u32 start, u32 n_out, int split3, u32 logn, cudaStream_t st);
+
+// key-switch inner product (key_switching_key.rs:256-268) on already transformed digits:
+// inter: [ct][n_dig][Lk][N] canonical NTT values; k0,k1: [n_dig][Lk][N];
+// out0/out1 row (ct, j) at out + (ct*out_ct_rows + j)*N ; base0/base1 (nullable) same indexing.
+void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* base0, const u64* base1, u64* out0,
+                  u64* out1, u32 cts, u32 n_dig, u32 Lk, u32 out_ct_rows, const RowIds& ids, const LimbDev* limbs,
+                  u32 logn, cudaStream_t st);
+
+// NTT-domain substitution gather (rq/mod.rs:368-377): out[row][t] = in[row][perm[t]]
+void launch_gather(const u64* in, u64* out, size_t n_rows, const int* perm, u32 logn, cudaStream_t st);
+
+// Poly<PowerBasis>::switch_down (rq/mod.rs:433-492): in [polys][L][N] -> out [polys][L-1][N]
+struct SwitchDownDev {
+  u64 q_last, q_last_half;
+  const u64* half_mod;  // [L-1]: q_i - (q_last/2 mod q_i)
+  const u64* inv;       // [L-1]: q_last^-1 mod q_i
+  const u64* inv_s;     // shoup
+};
+void launch_switch_down(const SwitchDownDev& S, const u64* in, u64* out, u32 polys, u32 L, const RowIds& ids,
+                        const LimbDev* limbs, u32 logn, cudaStream_t st);
+
+}  // namespace fhe_b200

@@ -1,0 +1,391 @@
+// Element-wise ring ops, tensor product, exact RNS scaler, key-switch inner product,
+// Galois gather and modulus switch-down kernels (sm_100a).  64-bit integer modular
+// arithmetic, HBM / integer-pipe bound: no tensor cores.
+#include "engine.hpp"
+
+namespace fhe_b200 {
+
+typedef unsigned __int128 u128;
+
+namespace {
+
+// ------------------------------------------------------------------ element-wise
+struct EwArgs {
+  u64* a;
+  const u64* b;
+  size_t n_words;
+  u32 logn, limbs_per_poly;
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+
+// Modulus::{add,sub,neg}_vec (zq/mod.rs:240-326, :534-550) over every row of a batch
+template <int OP>
+__global__ void ew_kernel(EwArgs A) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= A.n_words) return;
+  const u64 p = A.limbs[A.ids[(i >> A.logn) % A.limbs_per_poly]].p;
+  ulonglong2 x = *reinterpret_cast<ulonglong2*>(A.a + i);
+  if (OP == EW_NEG) {
+    x.x = csub(p - x.x, p);
+    x.y = csub(p - x.y, p);
+  } else {
+    ulonglong2 y = *reinterpret_cast<const ulonglong2*>(A.b + i);
+    if (OP == EW_ADD) {
+      x.x = csub(x.x + y.x, p);
+      x.y = csub(x.y + y.y, p);
+    } else {
+      x.x = csub(x.x + p - y.x, p);
+      x.y = csub(x.y + p - y.y, p);
+    }
+  }
+  *reinterpret_cast<ulonglong2*>(A.a + i) = x;
+}
+
+// ------------------------------------------------------------------ tensor
+struct TensorArgs {
+  const u64 *a, *b, *xa, *xb;
+  u64* out;
+  u32 cts, L, E, logn;
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+// c0 = a0*b0, c1 = a0*b1 + a1*b0, c2 = a1*b1 (bfv/ops/mul.rs:198-201; Modulus::mul_vec zq/mod.rs:332)
+__global__ void tensor_kernel(TensorArgs A) {
+  const u32 N = 1u << A.logn, K = A.L + A.E;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over cts*K*N
+  size_t total = (size_t)A.cts * K << A.logn;
+  if (idx >= total) return;
+  u32 c = idx & (N - 1);
+  size_t row = idx >> A.logn;
+  u32 pos = row % K, ct = row / K;
+  const LimbDev& M = A.limbs[A.ids[pos]];
+  u64 a0, a1, b0, b1;
+  if (pos < A.L) {
+    size_t o = (((size_t)ct * 2) * A.L + pos) << A.logn;
+    a0 = A.a[o + c]; a1 = A.a[o + ((size_t)A.L << A.logn) + c];
+    b0 = A.b[o + c]; b1 = A.b[o + ((size_t)A.L << A.logn) + c];
+  } else {
+    size_t o = (((size_t)ct * 2) * A.E + (pos - A.L)) << A.logn;
+    a0 = A.xa[o + c]; a1 = A.xa[o + ((size_t)A.E << A.logn) + c];
+    b0 = A.xb[o + c]; b1 = A.xb[o + ((size_t)A.E << A.logn) + c];
+  }
+  u64 c0 = mulmod(a0, b0, M.p, M.bhi, M.blo);
+  u64 c2 = mulmod(a1, b1, M.p, M.bhi, M.blo);
+  u128 s = (u128)a0 * b1 + (u128)a1 * b0;  // < 2^125
+  u64 c1 = barrett128((u64)s, (u64)(s >> 64), M.p, M.bhi, M.blo);
+  size_t o = (((size_t)ct * 3) * K + pos) << A.logn;
+  A.out[o + c] = c0;
+  A.out[o + ((size_t)K << A.logn) + c] = c1;
+  A.out[o + ((size_t)2 * K << A.logn) + c] = c2;
+}
+
+// ------------------------------------------------------------------ exact RNS scaler
+struct ScaleArgs {
+  ScalerDev S;
+  const LimbDev* limbs;
+  const u64* in;
+  u64 *out0, *out1;
+  u32 polys, out_rows_per_poly, start, n_out, split3, logn;
+};
+
+struct U256 {
+  u64 w0, w1, w2, w3;
+};
+__device__ __forceinline__ void u256_addmul(U256& s, u64 r, u64 lo, u64 hi, bool negate) {
+  // s +/-= r * (hi:lo)   (192-bit product, wrapping 256-bit accumulate; rns/scaler.rs:260-298)
+  u128 p0 = (u128)r * lo, p1 = (u128)r * hi;
+  u64 a0 = (u64)p0;
+  u128 mid = (p0 >> 64) + (u64)p1;
+  u64 a1 = (u64)mid;
+  u128 top = (mid >> 64) + (p1 >> 64);
+  u64 a2 = (u64)top, a3 = (u64)(top >> 64);
+  if (negate) {  // two's complement of the 256-bit product
+    a0 = ~a0; a1 = ~a1; a2 = ~a2; a3 = ~a3;
+    u128 c = (u128)a0 + 1; a0 = (u64)c;
+    c = (u128)a1 + (u64)(c >> 64); a1 = (u64)c;
+    c = (u128)a2 + (u64)(c >> 64); a2 = (u64)c;
+    a3 += (u64)(c >> 64);
+  }
+  u128 c = (u128)s.w0 + a0; s.w0 = (u64)c;
+  c = (u128)s.w1 + a1 + (u64)(c >> 64); s.w1 = (u64)c;
+  c = (u128)s.w2 + a2 + (u64)(c >> 64); s.w2 = (u64)c;
+  s.w3 = s.w3 + a3 + (u64)(c >> 64);
+}
+
+// One thread per (poly, coefficient): RnsScaler::scale (rns/scaler.rs:249-352) on the column
+// of n_from residues, writing n_out residues.  NF = compile-time bound on n_from.
+template <int NF>
+__global__ void scale_kernel(ScaleArgs A) {
+  extern __shared__ u64 smem[];
+  const ScalerDev& S = A.S;
+  const u32 nf = S.n_from, n_out = A.n_out;
+  u64* s_omega = smem;                        // [n_out][nf]
+  u64* s_gamma = s_omega + (size_t)n_out * nf;  // [n_out]
+  u64* s_tgl = s_gamma + n_out;               // theta_garner lo/hi [nf]
+  u64* s_tgh = s_tgl + nf;
+  u64* s_tol = s_tgh + nf;                    // theta_omega lo/hi/sign [nf]
+  u64* s_toh = s_tol + nf;
+  u64* s_tos = s_toh + nf;
+  for (u32 i = threadIdx.x; i < n_out * nf; i += blockDim.x)
+    s_omega[i] = S.omega[(size_t)(A.start + i / nf) * nf + i % nf];
+  for (u32 i = threadIdx.x; i < n_out; i += blockDim.x) s_gamma[i] = S.gamma[A.start + i];
+  for (u32 i = threadIdx.x; i < nf; i += blockDim.x) {
+    s_tgl[i] = S.tgar_lo[i];
+    s_tgh[i] = S.tgar_hi[i];
+    s_tol[i] = S.to_lo[i];
+    s_toh[i] = S.to_hi[i];
+    s_tos[i] = S.to_sign[i];
+  }
+  __syncthreads();
+
+  const u32 N = 1u << A.logn;
+  const u32 per_poly = N / blockDim.x;
+  const u32 poly = blockIdx.x / per_poly;
+  const u32 c = (blockIdx.x % per_poly) * blockDim.x + threadIdx.x;
+  const u64* src = A.in + (((size_t)poly * nf) << A.logn) + c;
+
+  u64 r[NF];
+#pragma unroll
+  for (int i = 0; i < NF; i++) r[i] = (u32)i < nf ? src[(size_t)i << A.logn] : 0;
+
+  // v = round(sum_i r_i * theta_garner_i / 2^shift)   (:260-272)
+  U256 sg = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < NF; i++)
+    if ((u32)i < nf) u256_addmul(sg, r[i], s_tgl[i], s_tgh[i], false);
+  u128 v;
+  {
+    // theta_garner_shift is in [123,127] for moduli < 2^62 and <= 64 limbs (rns/scaler.rs:130-142),
+    // so shift-1 = 64 + bs with 58 <= bs <= 62
+    const u32 bs = S.shift - 1 - 64;
+    u64 lo = (sg.w1 >> bs) | (sg.w2 << (64 - bs));
+    u64 hi = (sg.w2 >> bs) | (sg.w3 << (64 - bs));
+    u128 x = ((u128)hi << 64) | lo;
+    v = (x >> 1) + (x & 1);
+  }
+
+  // w = round((sum_i +/- r_i * theta_omega_i -/+ v * theta_gamma) / 2^127)   (:276-314)
+  bool w_sign = false;
+  u128 w = 0;
+  if (!S.is_one) {
+    U256 so = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < NF; i++)
+      if ((u32)i < nf) u256_addmul(so, r[i], s_tol[i], s_toh[i], s_tos[i] != 0);
+    // v * theta_gamma (128 x 128 -> 256), subtracted unless theta_gamma_sign
+    u256_addmul(so, (u64)v, S.tg_lo, S.tg_hi, !S.tg_sign);
+    {
+      // high half: (v >> 64) * theta_gamma << 64
+      U256 t = {0, 0, 0, 0};
+      u256_addmul(t, (u64)(v >> 64), S.tg_lo, S.tg_hi, false);
+      U256 sh = {0, t.w0, t.w1, t.w2};
+      if (!S.tg_sign) {  // negate
+        sh.w0 = ~sh.w0; sh.w1 = ~sh.w1; sh.w2 = ~sh.w2; sh.w3 = ~sh.w3;
+        u128 cc = (u128)sh.w0 + 1; sh.w0 = (u64)cc;
+        cc = (u128)sh.w1 + (u64)(cc >> 64); sh.w1 = (u64)cc;
+        cc = (u128)sh.w2 + (u64)(cc >> 64); sh.w2 = (u64)cc;
+        sh.w3 += (u64)(cc >> 64);
+      }
+      u128 cc = (u128)so.w0 + sh.w0; so.w0 = (u64)cc;
+      cc = (u128)so.w1 + sh.w1 + (u64)(cc >> 64); so.w1 = (u64)cc;
+      cc = (u128)so.w2 + sh.w2 + (u64)(cc >> 64); so.w2 = (u64)cc;
+      so.w3 = so.w3 + sh.w3 + (u64)(cc >> 64);
+    }
+    w_sign = (so.w3 != 0) || (so.w2 >> 63);
+    if (w_sign) {
+      u64 n1 = ~so.w1, n2 = ~so.w2, n3 = ~so.w3;
+      u128 x = ((u128)((n2 >> 62) | (n3 << 2)) << 64) | ((n1 >> 62) | (n2 << 2));
+      w = (x + 1) >> 1;
+    } else {
+      u128 x = ((u128)((so.w2 >> 62) | (so.w3 << 2)) << 64) | ((so.w1 >> 62) | (so.w2 << 2));
+      w = (x >> 1) + (x & 1);
+    }
+  }
+
+  // outputs (:316-351): y_j = (-(v mod q_j) * gamma_j +/- w + sum_i r_i * omega_ji) mod q_j
+  for (u32 j = 0; j < n_out; j++) {
+    const LimbDev& M = A.limbs[S.to_ids[A.start + j]];
+    Acc192 acc;
+    acc.clear();
+    const u64* om = s_omega + (size_t)j * nf;
+#pragma unroll
+    for (int i = 0; i < NF; i++)
+      if ((u32)i < nf) acc.mac(r[i], om[i]);
+    u64 vr = barrett128((u64)v, (u64)(v >> 64), M.p, M.bhi, M.blo);
+    acc.mac(vr ? M.p - vr : 0, s_gamma[j]);
+    if (!S.is_one) {
+      u64 wr = barrett128((u64)w, (u64)(w >> 64), M.p, M.bhi, M.blo);
+      acc.add64(w_sign ? (wr ? M.p - wr : 0) : wr);
+    }
+    u64 y = acc.reduce(M);
+    u64* dst;
+    if (A.split3) {
+      u32 ct = poly / 3, part = poly % 3;
+      dst = part < 2 ? A.out0 + ((((size_t)ct * 2 + part) * n_out + j) << A.logn)
+                     : A.out1 + (((size_t)ct * n_out + j) << A.logn);
+    } else {
+      dst = A.out0 + (((size_t)poly * A.out_rows_per_poly + j) << A.logn);
+    }
+    dst[c] = y;
+  }
+}
+
+// ------------------------------------------------------------------ key-switch MAC
+struct KsMacArgs {
+  const u64 *inter, *k0, *k1, *base0, *base1;
+  u64 *out0, *out1;
+  u32 cts, n_dig, Lk, out_ct_rows, logn;
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+// out0 = base0 + sum_i t_i * k0_i ; out1 = base1 + sum_i t_i * k1_i   (key_switching_key.rs:256-268)
+__global__ void ksmac_kernel(KsMacArgs A) {
+  const u32 N = 1u << A.logn;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over cts*Lk*N
+  size_t total = ((size_t)A.cts * A.Lk) << A.logn;
+  if (idx >= total) return;
+  u32 c = idx & (N - 1);
+  size_t row = idx >> A.logn;
+  u32 j = row % A.Lk, ct = row / A.Lk;
+  const LimbDev& M = A.limbs[A.ids[j]];
+  Acc192 a0, a1;
+  a0.clear();
+  a1.clear();
+  for (u32 i = 0; i < A.n_dig; i++) {
+    u64 t = A.inter[((((size_t)ct * A.n_dig + i) * A.Lk + j) << A.logn) + c];
+    size_t ko = (((size_t)i * A.Lk + j) << A.logn) + c;
+    a0.mac(t, __ldg(A.k0 + ko));
+    a1.mac(t, __ldg(A.k1 + ko));
+  }
+  size_t o = (((size_t)ct * A.out_ct_rows + j) << A.logn) + c;
+  if (A.base0) a0.add64(A.base0[o]);
+  if (A.base1) a1.add64(A.base1[o]);
+  A.out0[o] = a0.reduce(M);
+  A.out1[o] = a1.reduce(M);
+}
+
+// ------------------------------------------------------------------ gather / switch_down
+__global__ void gather_kernel(const u64* in, u64* out, size_t n_words, const int* perm, u32 logn) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_words) return;
+  size_t row = i >> logn;
+  u32 t = i & ((1u << logn) - 1);
+  out[i] = in[(row << logn) + perm[t]];
+}
+
+struct SwitchDownArgs {
+  SwitchDownDev S;
+  const u64* in;
+  u64* out;
+  u32 polys, L, logn;
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+__global__ void switch_down_kernel(SwitchDownArgs A) {
+  const u32 N = 1u << A.logn;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over polys*N
+  if (idx >= ((size_t)A.polys << A.logn)) return;
+  u32 c = idx & (N - 1);
+  size_t poly = idx >> A.logn;
+  const u64* src = A.in + ((poly * A.L) << A.logn) + c;
+  u64* dst = A.out + ((poly * (A.L - 1)) << A.logn) + c;
+  u64 xl = csub(src[(size_t)(A.L - 1) << A.logn] + A.S.q_last_half, A.S.q_last);  // rq/mod.rs:456-458
+  for (u32 i = 0; i + 1 < A.L; i++) {
+    const LimbDev& M = A.limbs[A.ids[i]];
+    u64 tmp = barrett64(xl, M.p, M.bhi, M.blo) + A.S.half_mod[i];   // :469
+    u64 v = src[(size_t)i << A.logn] + 3 * M.p - tmp;              // :473
+    dst[(size_t)i << A.logn] = mul_shoup(v, A.S.inv[i], A.S.inv_s[i], M.p);  // :476
+  }
+}
+
+void copy_ids(unsigned short* dst, const RowIds& ids) {
+  for (int i = 0; i < kMaxPos; i++) dst[i] = ids.ids[i];
+}
+
+}  // namespace
+
+void launch_ew(EwOp op, u64* a, const u64* b, size_t n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
+               cudaStream_t st) {
+  EwArgs A;
+  A.a = a;
+  A.b = b;
+  A.n_words = n_rows << logn;
+  A.logn = logn;
+  A.limbs_per_poly = ids.limbs_per_poly;
+  A.limbs = limbs;
+  copy_ids(A.ids, ids);
+  if (A.n_words == 0) return;
+  const u32 threads = 256;
+  const size_t blocks = (A.n_words / 2 + threads - 1) / threads;
+  if (op == EW_ADD) ew_kernel<EW_ADD><<<(unsigned)blocks, threads, 0, st>>>(A);
+  else if (op == EW_SUB) ew_kernel<EW_SUB><<<(unsigned)blocks, threads, 0, st>>>(A);
+  else ew_kernel<EW_NEG><<<(unsigned)blocks, threads, 0, st>>>(A);
+  g_launches++;
+}
+
+void launch_tensor(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 E,
+                   const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st) {
+  TensorArgs A;
+  A.a = a; A.b = b; A.xa = xa; A.xb = xb; A.out = out;
+  A.cts = cts; A.L = L; A.E = E; A.logn = logn;
+  A.limbs = limbs;
+  copy_ids(A.ids, mul_ids);
+  size_t total = ((size_t)cts * (L + E)) << logn;
+  if (!total) return;
+  tensor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+  g_launches++;
+}
+
+void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* out0, u64* out1, u32 polys,
+                  u32 out_rows_per_poly, u32 start, u32 n_out, int split3, u32 logn, cudaStream_t st) {
+  if (!polys || !n_out) return;
+  ScaleArgs A;
+  A.S = S; A.limbs = limbs; A.in = in; A.out0 = out0; A.out1 = out1;
+  A.polys = polys; A.out_rows_per_poly = out_rows_per_poly; A.start = start; A.n_out = n_out;
+  A.split3 = split3; A.logn = logn;
+  const u32 N = 1u << logn;
+  const u32 threads = N < 128 ? N : 128;
+  const unsigned blocks = polys * (N / threads);
+  const size_t smem = ((size_t)n_out * S.n_from + n_out + 5 * (size_t)S.n_from) * sizeof(u64);
+  if (S.n_from <= 4) scale_kernel<4><<<blocks, threads, smem, st>>>(A);
+  else if (S.n_from <= 8) scale_kernel<8><<<blocks, threads, smem, st>>>(A);
+  else if (S.n_from <= 16) scale_kernel<16><<<blocks, threads, smem, st>>>(A);
+  else if (S.n_from <= 32) scale_kernel<32><<<blocks, threads, smem, st>>>(A);
+  else scale_kernel<64><<<blocks, threads, smem, st>>>(A);
+  g_launches++;
+}
+
+void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* base0, const u64* base1, u64* out0,
+                  u64* out1, u32 cts, u32 n_dig, u32 Lk, u32 out_ct_rows, const RowIds& ids, const LimbDev* limbs,
+                  u32 logn, cudaStream_t st) {
+  KsMacArgs A;
+  A.inter = inter; A.k0 = k0; A.k1 = k1; A.base0 = base0; A.base1 = base1; A.out0 = out0; A.out1 = out1;
+  A.cts = cts; A.n_dig = n_dig; A.Lk = Lk; A.out_ct_rows = out_ct_rows; A.logn = logn;
+  A.limbs = limbs;
+  copy_ids(A.ids, ids);
+  size_t total = ((size_t)cts * Lk) << logn;
+  if (!total) return;
+  ksmac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+  g_launches++;
+}
+
+void launch_gather(const u64* in, u64* out, size_t n_rows, const int* perm, u32 logn, cudaStream_t st) {
+  size_t n = n_rows << logn;
+  if (!n) return;
+  gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, perm, logn);
+  g_launches++;
+}
+
+void launch_switch_down(const SwitchDownDev& S, const u64* in, u64* out, u32 polys, u32 L, const RowIds& ids,
+                        const LimbDev* limbs, u32 logn, cudaStream_t st) {
+  SwitchDownArgs A;
+  A.S = S; A.in = in; A.out = out; A.polys = polys; A.L = L; A.logn = logn; A.limbs = limbs;
+  copy_ids(A.ids, ids);
+  size_t total = (size_t)polys << logn;
+  if (!total) return;
+  switch_down_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+  g_launches++;
+}
+
+}  // namespace fhe_b200

@@ -1,0 +1,93 @@
+// NTT launcher: picks the (N1, N2) split and tile shapes for a given N and instantiates
+// the tile kernels of ntt.cuh.
+#include "engine.hpp"
+
+namespace fhe_b200 {
+
+std::atomic<unsigned long long> g_launches{0};
+
+namespace {
+
+constexpr int kTileLog = 12;  // 4096 words (32 KiB + padding) of shared memory per CTA
+
+template <int LOGP, int LOGB, bool INV>
+void run_rows(const NttArgs& a, cudaStream_t st) {
+  constexpr u32 T = 1u << (LOGP + LOGB);
+  const u32 tiles = (1u << a.logn1) >> LOGB;
+  const u32 threads = T / 8 >= 256 ? 256 : (T / 8 < 32 ? 32 : T / 8);
+  const size_t smem = (T + (T >> 5) + 1) * sizeof(u64);
+  ntt_rows_kernel<LOGP, LOGB, INV><<<a.n_rows * tiles, threads, smem, st>>>(a);
+  g_launches++;
+}
+template <int LOGP, int LOGB, bool INV>
+void run_cols(const NttArgs& a, cudaStream_t st) {
+  constexpr u32 T = 1u << (LOGP + LOGB);
+  const u32 tiles = (1u << (a.logn - LOGP)) >> LOGB;
+  const size_t smem = (T + (T >> 5) + 1) * sizeof(u64);
+  ntt_cols_kernel<LOGP, LOGB, INV><<<a.n_rows * tiles, 256, smem, st>>>(a);
+  g_launches++;
+}
+
+template <bool INV>
+void run_single(const NttArgs& a, cudaStream_t st) {
+  switch (a.logn) {
+    case 3: run_rows<3, 0, INV>(a, st); break;
+    case 4: run_rows<4, 0, INV>(a, st); break;
+    case 5: run_rows<5, 0, INV>(a, st); break;
+    case 6: run_rows<6, 0, INV>(a, st); break;
+    case 7: run_rows<7, 0, INV>(a, st); break;
+    case 8: run_rows<8, 0, INV>(a, st); break;
+    case 9: run_rows<9, 0, INV>(a, st); break;
+    case 10: run_rows<10, 0, INV>(a, st); break;
+    case 11: run_rows<11, 0, INV>(a, st); break;
+    case 12: run_rows<12, 0, INV>(a, st); break;
+    default: break;
+  }
+}
+template <bool INV>
+void run_cols_for(const NttArgs& a, cudaStream_t st) {
+  switch (a.logn1) {
+    case 7: run_cols<7, kTileLog - 7, INV>(a, st); break;
+    case 8: run_cols<8, kTileLog - 8, INV>(a, st); break;
+    case 9: run_cols<9, kTileLog - 9, INV>(a, st); break;
+    case 10: run_cols<10, kTileLog - 10, INV>(a, st); break;
+    default: break;
+  }
+}
+
+}  // namespace
+
+void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
+                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st) {
+  if (n_rows == 0) return;
+  NttArgs a;
+  a.in = in;
+  a.out = out;
+  a.limbs = limbs;
+  a.n_rows = n_rows;
+  a.limbs_per_poly = ids.limbs_per_poly;
+  a.in_div = in_div;
+  a.reduce_on_load = reduce_on_load ? 1 : 0;
+  a.logn = logn;
+  for (int i = 0; i < kMaxPos; i++) a.ids[i] = ids.ids[i];
+  if (logn <= 12) {
+    a.logn1 = 0;
+    if (inverse) run_single<true>(a, st); else run_single<false>(a, st);
+    return;
+  }
+  // two passes: N2 = 64 contiguous points (rows kernel), N1 = N / 64 (cols kernel)
+  a.logn1 = logn - 6;
+  NttArgs second = a;  // second pass runs in place on `out`
+  second.in = out;
+  second.in_div = 1;
+  second.reduce_on_load = 0;
+  if (!inverse) {
+    run_cols_for<false>(a, st);
+    run_rows<6, 6, false>(second, st);
+  } else {
+    run_rows<6, 6, true>(a, st);
+    run_cols_for<true>(second, st);
+  }
+}
+
+}  // namespace fhe_b200

@@ -1,0 +1,119 @@
+// Device-side arithmetic modulo one <=62-bit prime (sm_100a).
+// Mirrors the semantics of zq::Modulus in the reference
+// (crates/fhe-math/src/zq/mod.rs): Barrett with a 128-bit constant (:693),
+// Shoup multiplication (:224) and the single conditional subtraction (:659).
+// All API-visible results are canonical residues, so any correct reduction
+// strategy is bit-exact with the reference.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fhe_b200 {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// Per-limb constants + NTT tables; one entry per distinct prime of a parameter set.
+struct LimbDev {
+  u64 p;       // modulus
+  u64 p2;      // 2p
+  u64 bhi;     // floor(2^128 / p) >> 64          (zq/mod.rs:87-91)
+  u64 blo;     // floor(2^128 / p) & (2^64-1)
+  u64 ninv;    // N^-1 mod p                      (ntt/native.rs:39)
+  u64 ninv_s;  // shoup(N^-1)
+  u64 zn;      // zetas_inv[N-1] * N^-1 mod p  (last inverse stage fused with the N^-1 scaling)
+  u64 zn_s;    // shoup(zn)
+  u64 c128;    // 2^128 mod p (folds the third accumulator word of lazy sums)
+  u64 pad;
+  const u64* om;    // omegas[N]          = psi^{bitrev(i)}        (ntt/native.rs:50-56)
+  const u64* om_s;  // omegas_shoup[N]
+  const u64* zi;    // zetas_inv[N]       = psi^{-(bitrev(i)+1)}
+  const u64* zi_s;  // zetas_inv_shoup[N]
+};
+
+__device__ __forceinline__ u64 csub(u64 x, u64 p) { return x >= p ? x - p : x; }
+
+// lazy Shoup product: a*w mod p in [0,2p) for any 64-bit a (zq/mod.rs:224-234)
+__device__ __forceinline__ u64 mul_shoup_lazy(u64 a, u64 w, u64 ws, u64 p) {
+  u64 q = __umul64hi(a, ws);
+  return a * w - q * p;
+}
+__device__ __forceinline__ u64 mul_shoup(u64 a, u64 w, u64 ws, u64 p) {
+  return csub(mul_shoup_lazy(a, w, ws, p), p);
+}
+
+// device shoup(a) = floor(a * 2^64 / p), a < p (zq/mod.rs:195).  Uses the Barrett
+// constant: q ~ floor(a * floor(2^128/p) / 2^64), then fix up by at most 2.
+__device__ __forceinline__ u64 shoup_of(u64 a, u64 p, u64 bhi, u64 blo) {
+  // a * 2^64 / p: estimate with the 128-bit reciprocal
+  u64 q = a * bhi + __umul64hi(a, blo);  // floor(a*B / 2^64) low 64 bits, B = bhi*2^64+blo (a*bhi < 2^64 since a<p, bhi<=2^64/p*...)
+  // remainder r = a*2^64 - q*p (mod 2^64 arithmetic on the low word suffices: true r < 3p < 2^64)
+  u64 r = 0ull - q * p;  // low 64 bits of a*2^64 are 0
+  // r is in [0, 3p): correct q upward
+  if (r >= p) { r -= p; q++; }
+  if (r >= p) { r -= p; q++; }
+  return q;
+}
+
+// Barrett reduction of a 128-bit value (lo,hi) to [0,2p)  (zq/mod.rs:693-707)
+__device__ __forceinline__ u64 barrett128_lazy(u64 lo, u64 hi, u64 p, u64 bhi, u64 blo) {
+  // q = floor(((lo*bhi + hi*blo + (lo*blo >> 64)) >> 64) + hi*bhi
+  u64 t0 = __umul64hi(lo, blo);
+  u64 a_lo = lo * bhi, a_hi = __umul64hi(lo, bhi);
+  u64 b_lo = hi * blo, b_hi = __umul64hi(hi, blo);
+  // sum = a + b + t0 (up to 130 bits; we only need bits 64.. of the sum)
+  u64 s = a_lo + b_lo;
+  u64 c = s < a_lo;
+  u64 s2 = s + t0;
+  c += s2 < s;
+  u64 q = a_hi + b_hi + c + hi * bhi;  // low 64 bits of the quotient are all that matter
+  return lo - q * p;
+}
+__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, u64 p, u64 bhi, u64 blo) {
+  return csub(barrett128_lazy(lo, hi, p, bhi, blo), p);
+}
+// Barrett reduction of a 64-bit value to [0,p) (zq/mod.rs:712 + :659)
+__device__ __forceinline__ u64 barrett64(u64 a, u64 p, u64 bhi, u64 blo) {
+  // q = (a*bhi + (a*blo >> 64)) >> 64
+  u64 t0 = __umul64hi(a, blo);
+  u64 a_lo = a * bhi, a_hi = __umul64hi(a, bhi);
+  u64 s = a_lo + t0;
+  u64 q = a_hi + (s < a_lo);
+  return csub(a - q * p, p);
+}
+// a*b mod p, canonical
+__device__ __forceinline__ u64 mulmod(u64 a, u64 b, u64 p, u64 bhi, u64 blo) {
+  return barrett128(a * b, __umul64hi(a, b), p, bhi, blo);
+}
+
+// 192-bit lazy accumulator for sums of 64x64 products (used by the RNS scaler and the
+// key-switch inner product; replaces the reference's per-term Shoup reduction,
+// rns/scaler.rs:340-347 and rq/ops.rs:208, with one reduction at the end).
+struct Acc192 {
+  u64 lo, mid, hi;
+  __device__ __forceinline__ void clear() { lo = mid = hi = 0; }
+  __device__ __forceinline__ void mac(u64 a, u64 b) {
+    u64 pl = a * b, ph = __umul64hi(a, b);
+    lo += pl;
+    u64 c = lo < pl;
+    mid += c;
+    hi += mid < c;
+    mid += ph;
+    hi += mid < ph;
+  }
+  __device__ __forceinline__ void add64(u64 v) {
+    lo += v;
+    u64 c = lo < v;
+    mid += c;
+    hi += mid < c;
+  }
+  // canonical residue of the accumulated value; hi must be < 2^32
+  __device__ __forceinline__ u64 reduce(const LimbDev& m) const {
+    u64 r1 = barrett128_lazy(lo, mid, m.p, m.bhi, m.blo);  // [0,2p)
+    u64 hl = hi * m.c128, hh = __umul64hi(hi, m.c128);
+    u64 r2 = barrett128_lazy(hl, hh, m.p, m.bhi, m.blo);   // [0,2p)
+    return csub(csub(r1 + r2, m.p2), m.p);
+  }
+};
+
+}  // namespace fhe_b200

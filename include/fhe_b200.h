@@ -1,0 +1,178 @@
+/*
+ * fhe_b200.h -- C ABI of the B200-native BFV ciphertext-arithmetic engine.
+ *
+ * Drop-in boundary for the fhe-math / fhe::bfv hot path of tlepoint/fhe.rs @ e248cd28
+ * (pure Rust; it has no FFI of its own -- SURVEY.md section 8b).  Each entry point
+ * names the reference item it replaces (file:line under /root/reference/crates).
+ * A Rust host binds these with `extern "C"`; in this repository the
+ * same symbols are driven from C++ (include/fhe_b200.hpp) and Python ctypes
+ * (fhe_rs_b200/_capi.py).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all polynomial words are u64 residues.
+ *  - every call returns 0 on success or a negative fhe_b200_status mirroring the
+ *    reference's error enums (fhe-math/src/errors.rs:14-113, fhe/src/errors.rs:17-66);
+ *    nothing throws or aborts across the boundary.  fhe_b200_last_error() returns the
+ *    message of the calling thread's last failure.  (The reference's operators `+ - *`
+ *    panic on mismatched operands, ops/mod.rs:19-29; here the same conditions return
+ *    FHE_B200_CONTEXT_MISMATCH / FHE_B200_INVALID_LEVEL.)
+ *  - caller owns host memory; the library owns device memory behind opaque handles,
+ *    released by the matching *_destroy / *_free.  params and ksk handles are immutable
+ *    after creation and may be shared by host threads (like Arc<BfvParameters>,
+ *    bfv/parameters.rs:125); a batch handle must not be mutated concurrently.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Work is
+ *    enqueued asynchronously; fhe_b200_sync() or a download waits for it.
+ *  - host layout of a batch == Vec<u64>::from(&Poly) of the reference
+ *    (rq/convert.rs:474-503) concatenated over parts and ciphertexts:
+ *    [ciphertext][part][limb][coefficient], row-major, limb i modulo moduli[i].
+ *  - there is NO CPU fallback: compute entry points fail with FHE_B200_NO_DEVICE when the
+ *    parameter set was created without a CUDA device.
+ */
+#ifndef FHE_B200_H
+#define FHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  FHE_B200_OK = 0,
+  FHE_B200_INVALID_ARGUMENT = -1,       /* null pointer, zero count, bad size                        */
+  FHE_B200_INVALID_MODULUS = -2,        /* fhe_math::Error::InvalidModulus / NonCoprimeModuli        */
+  FHE_B200_INVALID_DEGREE = -3,         /* fhe_math::Error::InvalidPolynomialDegree                   */
+  FHE_B200_NTT_UNAVAILABLE = -4,        /* fhe_math::Error::NttOperatorUnavailable                    */
+  FHE_B200_CONTEXT_MISMATCH = -5,       /* PolynomialContextMismatch / fhe::Error::ParameterMismatch  */
+  FHE_B200_INVALID_LEVEL = -6,          /* fhe::Error::InvalidLevel / InvalidContextLevel             */
+  FHE_B200_BAD_POLY_COUNT = -7,         /* CiphertextError::{MultiplicationPolynomialCount,InvalidPolynomialCount} */
+  FHE_B200_INVALID_REPRESENTATION = -8, /* fhe_math::Error::IncorrectRepresentation                   */
+  FHE_B200_NO_MORE_CONTEXT = -9,        /* fhe_math::Error::NoMoreContext                             */
+  FHE_B200_INVALID_EXPONENT = -10,      /* fhe_math::Error::InvalidSubstitutionExponent               */
+  FHE_B200_UNSUPPORTED = -11,           /* feature outside the accelerated path                       */
+  FHE_B200_CUDA_ERROR = -20,
+  FHE_B200_OUT_OF_MEMORY = -21,
+  FHE_B200_NO_DEVICE = -22
+} fhe_b200_status;
+
+/* Poly representation tag (rq/mod.rs Representation). */
+typedef enum { FHE_B200_POWER_BASIS = 0, FHE_B200_NTT = 1 } fhe_b200_repr;
+
+typedef struct fhe_b200_params fhe_b200_params; /* == Arc<BfvParameters> (bfv/parameters.rs:88-114)            */
+typedef struct fhe_b200_batch fhe_b200_batch;   /* == Vec<Ciphertext> of one level (bfv/ciphertext.rs:18-32),
+                                                   device resident, [count][parts][limbs][N] u64               */
+typedef struct fhe_b200_ksk fhe_b200_ksk;       /* == KeySwitchingKey (bfv/keys/key_switching_key.rs:22-45)     */
+
+const char* fhe_b200_version(void);
+const char* fhe_b200_last_error(void);
+
+/* ---- parameters ---------------------------------------------------------------------
+ * BfvParametersBuilder::build (bfv/parameters.rs:560-738) for explicit moduli
+ * (`set_moduli`) or generated ones (`set_moduli_sizes`, parameters.rs:391-431).
+ * plaintext_le: plaintext modulus as little-endian bytes (as bfv.proto PlaintextBig).
+ * psi: optional 2N-th primitive roots, one per prime in the order
+ *      [moduli..., extended_basis...] (n_moduli + n_moduli + 1 entries); NULL selects the
+ *      documented default root.  A Rust host passes the reference's roots
+ *      (NttOperator.omegas[N/2], ntt/native.rs:50-56) so that NTT-domain data is
+ *      interchangeable bit for bit.
+ * device: CUDA device ordinal, or -1 for a host-only handle (table inspection only). */
+int fhe_b200_params_create(int device, uint32_t degree, const uint64_t* moduli, uint32_t n_moduli,
+                           const uint8_t* plaintext_le, uint32_t plaintext_len, const uint64_t* psi,
+                           fhe_b200_params** out);
+int fhe_b200_params_create_from_sizes(int device, uint32_t degree, const uint32_t* moduli_sizes,
+                                      uint32_t n_moduli, const uint8_t* plaintext_le,
+                                      uint32_t plaintext_len, fhe_b200_params** out);
+int fhe_b200_params_destroy(fhe_b200_params* p);
+uint32_t fhe_b200_params_degree(const fhe_b200_params* p);                 /* BfvParameters::degree          */
+uint32_t fhe_b200_params_n_moduli(const fhe_b200_params* p);               /* BfvParameters::moduli().len()  */
+int fhe_b200_params_moduli(const fhe_b200_params* p, uint64_t* out);       /* BfvParameters::moduli          */
+/* multiplication basis of `level`: the level's moduli followed by the extension primes
+ * (parameters.rs:660-700); *n receives the count, out may be NULL to query it. */
+int fhe_b200_params_mul_basis(const fhe_b200_params* p, uint32_t level, uint64_t* out, uint32_t* n);
+/* psi actually used for prime `q` of this parameter set. */
+int fhe_b200_params_psi(const fhe_b200_params* p, uint64_t q, uint64_t* psi);
+
+/* ---- batches --------------------------------------------------------------------------
+ * parts = polynomials per ciphertext (2 fresh, 3 after `&ct * &ct`); level = modulus-
+ * switching level (ciphertext.rs:31); limbs = n_moduli - level. */
+int fhe_b200_batch_alloc(const fhe_b200_params* p, uint32_t count, uint32_t parts, uint32_t level,
+                         int repr, fhe_b200_batch** out);
+int fhe_b200_batch_free(fhe_b200_batch* b);
+int fhe_b200_batch_info(const fhe_b200_batch* b, uint32_t* count, uint32_t* parts, uint32_t* level,
+                        uint32_t* limbs, int* repr);
+/* host <-> device copy of ciphertexts [first, first+n); host may be pageable or pinned. */
+int fhe_b200_batch_upload(fhe_b200_batch* b, uint32_t first, uint32_t n, const uint64_t* host, void* stream);
+int fhe_b200_batch_download(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint64_t* host, void* stream);
+/* Ciphertext::clone: dst <- src (same parameters, shape, level; representation is copied) */
+int fhe_b200_batch_copy(fhe_b200_batch* dst, const fhe_b200_batch* src, void* stream);
+/* raw device pointer of the batch storage (for zero-copy producers such as bench.py). */
+int fhe_b200_batch_device_ptr(const fhe_b200_batch* b, uint64_t** dptr, size_t* n_words);
+
+/* ---- keys -----------------------------------------------------------------------------
+ * KeySwitchingKey (key_switching_key.rs:22-45): c0, c1 are the NTT-domain values of the
+ * n_digits key polynomials at the key level, host layout [digit][limb][coeff];
+ * n_digits must equal the limb count of ciphertext_level (:113).  Shoup companions
+ * (Poly<NttShoup>) are not needed by the device inner product. */
+int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uint32_t ksk_level,
+                        const uint64_t* c0, const uint64_t* c1, uint32_t n_digits, fhe_b200_ksk** out);
+int fhe_b200_ksk_free(fhe_b200_ksk* k);
+
+/* ---- primitives (each parity-tested one by one) --------------------------------------- */
+/* Poly::into_ntt / NttOperator::forward[_vt] on every row (rq/mod.rs:535, ntt/native.rs:77,183) */
+int fhe_b200_ntt_forward(fhe_b200_batch* b, void* stream);
+/* Poly::into_power_basis / NttOperator::backward[_vt] (rq/mod.rs:590, ntt/native.rs:106,197) */
+int fhe_b200_ntt_backward(fhe_b200_batch* b, void* stream);
+/* Ciphertext += / -= / unary - (bfv/ops/mod.rs:54, :148, :205; rq/ops.rs:92-172, :354-418) */
+int fhe_b200_add(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream);
+int fhe_b200_sub(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream);
+int fhe_b200_neg(fhe_b200_batch* a, void* stream);
+/* &Ciphertext * &Ciphertext, 2 parts x 2 parts -> 3 parts (bfv/ops/mod.rs:259-358) */
+int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batch* out3, void* stream);
+/* RelinearizationKey::relinearizes: (c0,c1,c2) -> (c0,c1) (keys/relinearization_key.rs:70-103) */
+int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_b200_batch* out2, void* stream);
+/* Multiplicator::default(rk).multiply (bfv/ops/mul.rs:101-138, :165-243); mod_switch != 0
+ * additionally applies Ciphertext::switch_down (mul.rs:238) and out2 must be at level+1. */
+int fhe_b200_mul_relin(const fhe_b200_batch* a, const fhe_b200_batch* b, const fhe_b200_ksk* rk,
+                       int mod_switch, fhe_b200_batch* out2, void* stream);
+/* GaloisKey::relinearize (keys/galois_key.rs:63-86) for substitution exponent `exponent`
+ * (column rotation by i <-> 3^i mod 2N, row swap <-> 2N-1; evaluation_key.rs:118, :278-286) */
+int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_ksk* gk,
+                    fhe_b200_batch* out, void* stream);
+/* Poly::substitute on every row of an NTT batch (rq/mod.rs:360-389) */
+int fhe_b200_substitute(const fhe_b200_batch* in, uint32_t exponent, fhe_b200_batch* out, void* stream);
+/* Ciphertext::switch_down: drop the last modulus with rounding (ciphertext.rs:148-161, rq/mod.rs:433-492) */
+int fhe_b200_switch_down(fhe_b200_batch* b, void* stream);
+/* KeySwitchingKey::key_switch on part `part` of a POWER_BASIS batch (key_switching_key.rs:241-270):
+ * out (2 parts, NTT, ksk level) = (sum_i NTT(d_i) * c0_i, sum_i NTT(d_i) * c1_i) */
+int fhe_b200_key_switch(const fhe_b200_batch* pb, uint32_t part, const fhe_b200_ksk* k,
+                        fhe_b200_batch* out2, void* stream);
+/* rq::scaler::Scaler::scale with the level's multiplication scalers (rq/scaler.rs:55-127):
+ * which = 0: extender (level basis -> multiplication basis, factor 1),
+ * which = 1: down scaler (multiplication basis -> level basis, factor t/Q).
+ * `in` is an NTT batch whose limb count equals the source basis; out gets the target basis. */
+int fhe_b200_scale(const fhe_b200_batch* in, int which, fhe_b200_batch* out, void* stream);
+/* batch over the multiplication basis of `level` (limbs = L + E), for fhe_b200_scale */
+int fhe_b200_batch_alloc_mul_basis(const fhe_b200_params* p, uint32_t count, uint32_t parts, uint32_t level,
+                                   int repr, fhe_b200_batch** out);
+
+int fhe_b200_sync(void* stream);
+/* kernels launched by this library in the calling process so far (bench.py "gpu_launches") */
+uint64_t fhe_b200_launch_count(void);
+
+/* ---- inspection of the host precompute (CPU-only tests of the parameter builder) -------
+ * RnsScaler tables (rns/scaler.rs:52-73) of the level's extender (which=0) / down scaler
+ * (which=1).  Any output pointer may be NULL.  omega is [n_to][n_from]. */
+int fhe_b200_debug_scaler_tables(const fhe_b200_params* p, uint32_t level, int which, uint32_t* n_from,
+                                 uint32_t* n_to, uint32_t* shift, uint64_t* gamma, uint64_t* omega,
+                                 uint64_t* theta_gamma /* lo,hi,sign */, uint64_t* theta_omega_lo,
+                                 uint64_t* theta_omega_hi, uint8_t* theta_omega_sign,
+                                 uint64_t* theta_garner_lo, uint64_t* theta_garner_hi);
+/* NTT tables of prime q: any of omegas/zetas_inv (N words each) may be NULL. */
+int fhe_b200_debug_ntt_tables(const fhe_b200_params* p, uint64_t q, uint64_t* omegas, uint64_t* omegas_shoup,
+                              uint64_t* zetas_inv, uint64_t* zetas_inv_shoup, uint64_t* size_inv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FHE_B200_H */

@@ -952,6 +952,20 @@ class KeySwitchingKey:
             b.iadd(frm.mul_scalar_big(rns.garner[i]))
             self.c0.append(b.into_ntt_shoup())
 
+    @staticmethod
+    def from_arrays(par: BfvParameters, c0: np.ndarray, c1: np.ndarray, ciphertext_level: int = 0,
+                    ksk_level: int = 0) -> "KeySwitchingKey":
+        """Rebuild a key from its NTT-domain words (as TryConvertFrom<&KeySwitchingKeyProto>,
+        key_switching_key.rs:418-482, minus the seed expansion)."""
+        k = KeySwitchingKey.__new__(KeySwitchingKey)
+        k.par = par
+        k.ctx_ksk = par.context_at_level(ksk_level)
+        k.ctx_ciphertext = par.context_at_level(ciphertext_level)
+        k.ciphertext_level, k.ksk_level = ciphertext_level, ksk_level
+        k.c0 = [Poly(k.ctx_ksk, NTT_SHOUP, a) for a in c0]
+        k.c1 = [Poly(k.ctx_ksk, NTT_SHOUP, a) for a in c1]
+        return k
+
     def key_switch(self, p: Poly):  # :241-270
         assert p.ctx == self.ctx_ciphertext and p.rep == POWER_BASIS
         c0 = Poly(self.ctx_ksk, NTT)
@@ -989,6 +1003,12 @@ class RelinearizationKey:
         s2 = s.mul(s).into_power_basis()
         s2_up = Switcher(ctx_ct, ctx_rk).switch(s2)
         self.ksk = KeySwitchingKey(sk, s2_up, ciphertext_level, key_level, rng)
+
+    @staticmethod
+    def from_ksk(ksk: "KeySwitchingKey") -> "RelinearizationKey":
+        rk = RelinearizationKey.__new__(RelinearizationKey)
+        rk.ksk = ksk
+        return rk
 
     def relinearizes(self, ct: Ciphertext) -> Ciphertext:  # :70-103
         assert len(ct.c) == 3 and ct.level == self.ksk.ciphertext_level

@@ -1,0 +1,276 @@
+"""GPU parity tests: every C-ABI operation of libfhe_b200.so (driven through the host
+mirror fhe_rs_b200.bfv, i.e. through the C ABI) must be BIT-EXACT against the CPU oracle
+on identical inputs.  Mirrors the reference's own tests (ntt/mod.rs:50-82,
+rq/scaler.rs:153-204, bfv/ops/mul.rs:263-330, keys/*.rs tests).  Run with `-m gpu`."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import fhe_rs_b200
+    return fhe_rs_b200
+
+
+def make_pair(oracle, F, degree, nmod, t, seed, sizes=None):
+    opar = oracle.BfvParameters(degree, t, moduli_sizes=sizes or [62] * nmod)
+    gpar = F.BfvParameters(degree, t, moduli=opar.moduli, device=0)
+    assert gpar.moduli() == opar.moduli
+    assert gpar.mul_basis(0) == opar.level(0).mul_params.to.moduli
+    return opar, gpar, np.random.default_rng(seed)
+
+
+def rand_ct(oracle, opar, rng, count, parts=2, level=0):
+    ctx = opar.context_at_level(level)
+    arr = np.zeros((count, parts, len(ctx.moduli), opar.degree), np.uint64)
+    for i, q in enumerate(ctx.moduli):
+        arr[:, :, i, :] = rng.integers(0, q, size=(count, parts, opar.degree), dtype=np.uint64)
+    return arr
+
+
+@pytest.mark.parametrize("logn,nmod", [(3, 2), (4, 3), (6, 2), (9, 2), (10, 3), (11, 2), (12, 2), (13, 2), (14, 3),
+                                        (15, 2), (16, 1)])
+def test_ntt_forward_backward(oracle, F, logn, nmod):
+    """NttOperator::forward/backward (ntt/native.rs:77-233) on every row of a batch."""
+    n = 1 << logn
+    opar, gpar, rng = make_pair(oracle, F, n, nmod, 1153 if logn < 12 else 786433, 10 + logn)
+    ctx = opar.context_at_level(0)
+    x = rand_ct(oracle, opar, rng, 3)
+    ct = F.Ciphertext.from_host(gpar, x, repr=F.POWER_BASIS)
+    got = ct.into_ntt().to_host()
+    exp = x.copy()
+    for c in range(3):
+        for p in range(2):
+            for i, op in enumerate(ctx.ops):
+                op.forward(exp[c, p, i])
+    assert (got == exp).all()
+    back = ct.into_power_basis().to_host()
+    assert (back == x).all()
+    # backward on arbitrary (reduced) NTT-domain input
+    ct2 = F.Ciphertext.from_host(gpar, x, repr=F.NTT)
+    got = ct2.into_power_basis().to_host()
+    exp = x.copy()
+    for c in range(3):
+        for p in range(2):
+            for i, op in enumerate(ctx.ops):
+                op.backward(exp[c, p, i])
+    assert (got == exp).all()
+    with pytest.raises(F.FheError) as e:
+        ct2.into_power_basis()
+    assert e.value.code == -8
+
+
+def test_add_sub_neg(oracle, F):
+    """ops/mod.rs:15-227"""
+    opar, gpar, rng = make_pair(oracle, F, 64, 3, 1153, 1)
+    a, b = rand_ct(oracle, opar, rng, 5), rand_ct(oracle, opar, rng, 5)
+    A, B = F.Ciphertext.from_host(gpar, a), F.Ciphertext.from_host(gpar, b)
+    q = np.array(opar.moduli, dtype=object)[None, None, :, None]
+    ao, bo = a.astype(object), b.astype(object)
+    assert ((A + B).to_host().astype(object) == (ao + bo) % q).all()
+    assert ((A - B).to_host().astype(object) == (ao - bo) % q).all()
+    assert ((-A).to_host().astype(object) == (-ao) % q).all()
+    # mismatched levels are rejected (ops/mod.rs:28)
+    C1 = F.Ciphertext(gpar, 5, 2, level=1)
+    with pytest.raises(F.FheError) as e:
+        A += C1
+    assert e.value.code == -6
+
+
+@pytest.mark.parametrize("degree,nmod", [(16, 2), (16, 5), (64, 3), (4096, 2)])
+def test_scalers(oracle, F, degree, nmod):
+    """rq::scaler::Scaler::scale (rq/scaler.rs:55-127) with the multiplication scalers."""
+    t = 1153 if degree < 4096 else 1032193
+    opar, gpar, rng = make_pair(oracle, F, degree, nmod, t, 2 + nmod)
+    mp = opar.level(0).mul_params
+    x = rand_ct(oracle, opar, rng, 2)
+    ct = F.Ciphertext.from_host(gpar, x)
+    up = ct.scale(0)
+    got = up.to_host()
+    for c in range(2):
+        for p in range(2):
+            exp = mp.extender.scale(oracle.Poly(mp.frm, oracle.NTT, x[c, p])).c
+            assert (got[c, p] == exp).all()
+    # down scaler on random data in the multiplication basis
+    K = len(mp.to.moduli)
+    y = np.zeros((2, 2, K, degree), np.uint64)
+    for i, q in enumerate(mp.to.moduli):
+        y[:, :, i, :] = rng.integers(0, q, size=(2, 2, degree), dtype=np.uint64)
+    cty = F.Ciphertext.from_host(gpar, y, mul_basis=True)
+    got = cty.scale(1).to_host()
+    for c in range(2):
+        for p in range(2):
+            exp = mp.down_scaler.scale(oracle.Poly(mp.to, oracle.NTT, y[c, p])).c
+            assert (got[c, p] == exp).all()
+
+
+def _keys(oracle, F, opar, gpar, rng, exponents=(), ct_level=0, key_level=0):
+    sk = oracle.SecretKey(opar, rng)
+    ork = oracle.RelinearizationKey(sk, rng, ct_level, key_level)
+    grk = F.RelinearizationKey.from_arrays(gpar, *ork.ksk.arrays(), ciphertext_level=ct_level, key_level=key_level)
+    ogk, ggk = {}, {}
+    for e in exponents:
+        ogk[e] = oracle.GaloisKey(sk, e, rng, ct_level, key_level)
+        ggk[e] = F.GaloisKey.from_arrays(gpar, e, *ogk[e].ksk.arrays(), ciphertext_level=ct_level, key_level=key_level)
+    return sk, ork, grk, ogk, ggk
+
+
+@pytest.mark.parametrize("degree,nmod,t", [(16, 2, 1153), (16, 3, 1153), (16, 5, 1153), (128, 3, 1153),
+                                           (4096, 2, 1032193)])
+def test_mul_relin_against_oracle(oracle, F, degree, nmod, t):
+    """&ct * &ct (ops/mod.rs:259-358), RelinearizationKey::relinearizes (relinearization_key.rs:70-103),
+    Multiplicator::multiply with and without mod switching (mul.rs:165-243): bit-exact, and the
+    result decrypts to the negacyclic product (mul.rs:263-330)."""
+    opar, gpar, rng = make_pair(oracle, F, degree, nmod, t, 40 + nmod)
+    sk, ork, grk, _, _ = _keys(oracle, F, opar, gpar, rng)
+    count = 3
+    msgs_a = rng.integers(0, t, size=(count, degree))
+    msgs_b = rng.integers(0, t, size=(count, degree))
+    octa = [sk.encrypt(m, 0, rng) for m in msgs_a]
+    octb = [sk.encrypt(m, 0, rng) for m in msgs_b]
+    a = np.stack([c.to_array() for c in octa])
+    b = np.stack([c.to_array() for c in octb])
+    A, B = F.Ciphertext.from_host(gpar, a), F.Ciphertext.from_host(gpar, b)
+
+    C3 = A * B
+    assert len(C3) == 3
+    got3 = C3.to_host()
+    for i in range(count):
+        assert (got3[i] == octa[i].mul(octb[i]).to_array()).all()
+
+    got2 = grk.relinearizes(C3).to_host()
+    om = oracle.Multiplicator.default(ork)
+    gm = F.Multiplicator.default(grk)
+    gotm = gm.multiply(A, B).to_host()
+    for i in range(count):
+        exp = om.multiply(octa[i], octb[i])
+        assert (gotm[i] == exp.to_array()).all()
+        assert (got2[i] == exp.to_array()).all()
+    # decrypt-correctness of the GPU result (schoolbook check only at small degree)
+    if degree <= 128:
+        res = oracle.Ciphertext.from_array(opar, gotm[0], 0)
+        dec = sk.decrypt(res)
+        exp = np.zeros(degree, dtype=object)
+        for x in range(degree):
+            for y in range(degree):
+                k, v = x + y, int(msgs_a[0][x]) * int(msgs_b[0][y])
+                if k < degree:
+                    exp[k] = (exp[k] + v) % t
+                else:
+                    exp[k - degree] = (exp[k - degree] - v) % t
+        assert (dec.astype(object) == exp).all()
+    # with modulus switching (mul.rs:296-330)
+    om.enable_mod_switching()
+    gm.enable_mod_switching()
+    out = gm.multiply(A, B)
+    assert out.level == 1
+    gotms = out.to_host()
+    for i in range(count):
+        assert (gotms[i] == om.multiply(octa[i], octb[i]).to_array()).all()
+    # error behaviour: wrong part count / level (mul.rs:168-189)
+    with pytest.raises(F.FheError) as e:
+        gm.multiply(C3, B)
+    assert e.value.code == -7
+    with pytest.raises(F.FheError) as e:
+        gm.multiply(out, out)
+    assert e.value.code == -6
+
+
+@pytest.mark.parametrize("degree,nmod", [(16, 3), (64, 2), (4096, 2)])
+def test_galois_and_key_switch(oracle, F, degree, nmod):
+    """GaloisKey::relinearize (galois_key.rs:63-86), Poly::substitute (rq/mod.rs:360-389),
+    KeySwitchingKey::key_switch (key_switching_key.rs:241-270), rotation semantics (:211-230)."""
+    t = 1153 if degree < 4096 else 1032193
+    opar, gpar, rng = make_pair(oracle, F, degree, nmod, t, 60 + nmod)
+    exps = (3, 2 * degree - 1, 9)
+    sk, ork, grk, ogk, ggk = _keys(oracle, F, opar, gpar, rng, exps)
+    count = 2
+    vals = rng.integers(0, t, size=(count, degree))
+    octs = [sk.encrypt(oracle.simd_encode(opar, v), 0, rng) for v in vals]
+    x = np.stack([c.to_array() for c in octs])
+    X = F.Ciphertext.from_host(gpar, x)
+    for e in exps:
+        got = ggk[e].relinearize(X).to_host()
+        for i in range(count):
+            assert (got[i] == ogk[e].relinearize(octs[i]).to_array()).all()
+        sub = X.substitute(e).to_host()
+        for i in range(count):
+            for p in range(2):
+                assert (sub[i, p] == octs[i].c[p].substitute(e).c).all()
+    with pytest.raises(F.FheError) as err:
+        X.substitute(4)
+    assert err.value.code == -10
+    # EvaluationKey rotations decrypt to the expected slot permutation
+    ek = F.EvaluationKey(gpar)
+    for e in exps:
+        ek.add_galois_key(ggk[e])
+    row = degree // 2
+    got = ek.rotates_columns_by(X, 1).to_host()
+    dec = oracle.simd_decode(opar, sk.decrypt(oracle.Ciphertext.from_array(opar, got[0], 0)))
+    assert (dec == np.concatenate([np.roll(vals[0][:row], -1), np.roll(vals[0][row:], -1)])).all()
+    got = ek.rotates_rows(X).to_host()
+    dec = oracle.simd_decode(opar, sk.decrypt(oracle.Ciphertext.from_array(opar, got[0], 0)))
+    assert (dec == np.concatenate([vals[0][row:], vals[0][:row]])).all()
+    # raw key switch of a power-basis polynomial
+    pb = F.Ciphertext.from_host(gpar, x).into_power_basis()
+    ks = grk.ksk.key_switch(pb, part=1).to_host()
+    for i in range(count):
+        p = octs[i].c[1].copy().into_power_basis()
+        c0, c1 = ork.ksk.key_switch(p)
+        assert (ks[i, 0] == c0.c).all() and (ks[i, 1] == c1.c).all()
+
+
+def test_switch_down(oracle, F):
+    """Ciphertext::switch_down (ciphertext.rs:148-161, rq/mod.rs:433-492)"""
+    opar, gpar, rng = make_pair(oracle, F, 32, 4, 1153, 77)
+    x = rand_ct(oracle, opar, rng, 3)
+    X = F.Ciphertext.from_host(gpar, x)
+    X.switch_down()
+    assert X.level == 1 and X.limbs == 3
+    got = X.to_host()
+    for i in range(3):
+        exp = oracle.Ciphertext.from_array(opar, x[i], 0).switch_down()
+        assert (got[i] == exp.to_array()).all()
+    X.switch_down().switch_down()
+    with pytest.raises(F.FheError) as e:
+        X.switch_down()
+    assert e.value.code == -9
+
+
+def test_mixed_modulus_sizes(oracle, F):
+    """non-62-bit moduli (default_parameters_128 style, parameters.rs:224-250): generic Barrett/Shoup path."""
+    moduli = [0xffffee001, 0xffffc4001, 0x1ffffe0001]
+    t = 65537
+    opar = oracle.BfvParameters(4096, t, moduli=moduli)
+    gpar = F.BfvParameters(4096, t, moduli=moduli)
+    rng = np.random.default_rng(5)
+    sk, ork, grk, _, _ = _keys(oracle, F, opar, gpar, rng)
+    ma, mb = rng.integers(0, t, 4096), rng.integers(0, t, 4096)
+    ca, cb = sk.encrypt(ma, 0, rng), sk.encrypt(mb, 0, rng)
+    A = F.Ciphertext.from_host(gpar, ca.to_array()[None])
+    B = F.Ciphertext.from_host(gpar, cb.to_array()[None])
+    got = F.Multiplicator.default(grk).multiply(A, B).to_host()
+    assert (got[0] == oracle.Multiplicator.default(ork).multiply(ca, cb).to_array()).all()
+
+
+def test_golden_fixture(oracle, F):
+    """committed golden vectors (tests/golden/make_golden.py): GPU == stored outputs, no oracle involved"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_n16_l3.npz"))
+    gpar = F.BfvParameters(int(g["degree"]), int(g["t"]), moduli=[int(x) for x in g["moduli"]],
+                           psi=[int(x) for x in g["psi"]])
+    A, B = F.Ciphertext.from_host(gpar, g["a"]), F.Ciphertext.from_host(gpar, g["b"])
+    rk = F.RelinearizationKey.from_arrays(gpar, g["rk_c0"], g["rk_c1"])
+    gk = F.GaloisKey.from_arrays(gpar, 3, g["gk_c0"], g["gk_c1"])
+    assert ((A + B).to_host() == g["add"]).all()
+    assert ((A * B).to_host() == g["mul3"]).all()
+    m = F.Multiplicator.default(rk)
+    assert (m.multiply(A, B).to_host() == g["mul_relin"]).all()
+    assert (m.enable_mod_switching().multiply(A, B).to_host() == g["mul_relin_ms"]).all()
+    assert (gk.relinearize(A).to_host() == g["galois3"]).all()
+    assert (F.Ciphertext.from_host(gpar, g["a"]).into_power_basis().to_host() == g["a_pb"]).all()
