@@ -205,6 +205,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import fhe_rs_b200 as F
+    from fhe_rs_b200._capi import check
     L = F._capi.lib()
 
     # BfvParametersBuilder::set_moduli_sizes(&[62; 14]) -> the library generates the primes (parameters.rs:391)
@@ -225,7 +226,7 @@ def main():
     out = F.Ciphertext(par, B, 2)
 
     def step():
-        F.check(L.fhe_b200_mul_relin(A._h, Bt._h, rk.ksk._h, 0, out._h, None))
+        check(L.fhe_b200_mul_relin(A._h, Bt._h, rk.ksk._h, 0, out._h, None))
 
     def barrier():
         torch.cuda.synchronize()
@@ -266,10 +267,10 @@ def main():
     Ae, Bte, oute = F.Ciphertext(par, Be, 2), F.Ciphertext(par, Be, 2), F.Ciphertext(par, Be, 2)
 
     def e2e_step():
-        F.check(L.fhe_b200_batch_upload(Ae._h, 0, Be, ha.data_ptr(), None))
-        F.check(L.fhe_b200_batch_upload(Bte._h, 0, Be, hb.data_ptr(), None))
-        F.check(L.fhe_b200_mul_relin(Ae._h, Bte._h, rk.ksk._h, 0, oute._h, None))
-        F.check(L.fhe_b200_batch_download(oute._h, 0, Be, ho.data_ptr(), None))   # synchronises
+        check(L.fhe_b200_batch_upload(Ae._h, 0, Be, ha.data_ptr(), None))
+        check(L.fhe_b200_batch_upload(Bte._h, 0, Be, hb.data_ptr(), None))
+        check(L.fhe_b200_mul_relin(Ae._h, Bte._h, rk.ksk._h, 0, oute._h, None))
+        check(L.fhe_b200_batch_download(oute._h, 0, Be, ho.data_ptr(), None))   # synchronises
 
     e2e_step()
     barrier()

@@ -1,6 +1,7 @@
 // C ABI of the engine (include/fhe_b200.h): parameter precompute + upload, device batches,
 // key material, and the batched homomorphic operations built from the kernels of
 // ntt.cu / kernels.cu.  No CPU fallback: compute entry points require a CUDA device.
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -35,6 +36,10 @@ struct LevelData {
 }  // namespace
 
 struct fhe_b200_params {
+  // Arc-like lifetime (the reference shares Arc<BfvParameters>): batches and keys hold a
+  // reference, so the tables outlive every handle that points at them regardless of the order
+  // in which a garbage-collected host releases its objects.
+  std::atomic<int> refs{1};
   int device = -1;
   u32 N = 0, logn = 0, Lmax = 0;
   std::vector<u64> moduli, ext, primes, psi;
@@ -166,6 +171,21 @@ struct fhe_b200_ksk {
 };
 
 namespace {
+
+void params_release(const fhe_b200_params* cp) {
+  fhe_b200_params* p = const_cast<fhe_b200_params*>(cp);
+  if (!p || p->refs.fetch_sub(1) != 1) return;
+  if (p->device >= 0) {
+    cudaSetDevice(p->device);
+    for (void* d : p->d_allocs) cudaFree(d);
+    cudaGetLastError();
+  }
+  delete p;
+}
+const fhe_b200_params* params_retain(const fhe_b200_params* p) {
+  const_cast<fhe_b200_params*>(p)->refs.fetch_add(1);
+  return p;
+}
 
 struct DeviceGuard {
   explicit DeviceGuard(const fhe_b200_params* p) {
@@ -384,12 +404,7 @@ int fhe_b200_params_create_from_sizes(int device, uint32_t degree, const uint32_
 }
 
 int fhe_b200_params_destroy(fhe_b200_params* p) {
-  if (!p) return FHE_B200_OK;
-  if (p->device >= 0) {
-    cudaSetDevice(p->device);
-    for (void* d : p->d_allocs) cudaFree(d);
-  }
-  delete p;
+  params_release(p);
   return FHE_B200_OK;
 }
 uint32_t fhe_b200_params_degree(const fhe_b200_params* p) { return p ? p->N : 0; }
@@ -430,6 +445,7 @@ static int batch_alloc(const fhe_b200_params* p, uint32_t count, uint32_t parts,
   b->limbs = mul_basis ? lv.K : lv.L;
   b->d = nullptr;
   FHE_CUDA(cudaMalloc(&b->d, b->words_per_ct() * count * sizeof(u64)));
+  params_retain(p);
   *out = b.release();
   API_END
 }
@@ -445,6 +461,8 @@ int fhe_b200_batch_free(fhe_b200_batch* b) {
   if (!b) return FHE_B200_OK;
   if (b->par->device >= 0) cudaSetDevice(b->par->device);
   cudaFree(b->d);
+  cudaGetLastError();
+  params_release(b->par);
   delete b;
   return FHE_B200_OK;
 }
@@ -514,6 +532,7 @@ int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uin
   FHE_CUDA(cudaMalloc(&k->k1, bytes));
   FHE_CUDA(cudaMemcpy(k->k0, c0, bytes, cudaMemcpyHostToDevice));
   FHE_CUDA(cudaMemcpy(k->k1, c1, bytes, cudaMemcpyHostToDevice));
+  params_retain(p);
   *out = k.release();
   API_END
 }
@@ -522,6 +541,8 @@ int fhe_b200_ksk_free(fhe_b200_ksk* k) {
   if (k->par->device >= 0) cudaSetDevice(k->par->device);
   cudaFree(k->k0);
   cudaFree(k->k1);
+  cudaGetLastError();
+  params_release(k->par);
   delete k;
   return FHE_B200_OK;
 }

@@ -131,7 +131,8 @@ inline NttTablesH make_ntt_tables(u64 p, size_t n, u64 psi) {
     t.om_s[i] = m.shoup(t.om[i]);
     t.zi_s[i] = m.shoup(t.zi[i]);
   }
-  t.zn = mulmod_h(t.zi[n - 1], t.ninv, p);
+  // the last inverse stage (l = N/2, one block) consumes zetas_inv[N-2] (k runs 0..N-2, native.rs:201-227)
+  t.zn = mulmod_h(t.zi[n - 2], t.ninv, p);
   t.zn_s = m.shoup(t.zn);
   return t;
 }

@@ -21,7 +21,7 @@ struct LimbDev {
   u64 blo;     // floor(2^128 / p) & (2^64-1)
   u64 ninv;    // N^-1 mod p                      (ntt/native.rs:39)
   u64 ninv_s;  // shoup(N^-1)
-  u64 zn;      // zetas_inv[N-1] * N^-1 mod p  (last inverse stage fused with the N^-1 scaling)
+  u64 zn;      // zetas_inv[N-2] * N^-1 mod p  (last inverse stage fused with the N^-1 scaling)
   u64 zn_s;    // shoup(zn)
   u64 c128;    // 2^128 mod p (folds the third accumulator word of lazy sums)
   u64 pad;

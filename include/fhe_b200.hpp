@@ -1,0 +1,247 @@
+// fhe_b200.hpp -- C++17 host-side mirror of the reference's `fhe::bfv` interface for the
+// accelerated path, header-only, implemented purely on the C ABI of fhe_b200.h.
+//
+// Names and argument meaning follow tlepoint/fhe.rs (paths under /root/reference/crates/fhe/src):
+//   bfv::BfvParameters / BfvParametersBuilder   bfv/parameters.rs:88, :319
+//   bfv::Ciphertext                             bfv/ciphertext.rs:18  (here: a device-resident batch)
+//   bfv::KeySwitchingKey / RelinearizationKey   bfv/keys/key_switching_key.rs:22, relinearization_key.rs:23
+//   bfv::GaloisKey / EvaluationKey              bfv/keys/galois_key.rs:18, evaluation_key.rs:110-170
+//   bfv::Multiplicator                          bfv/ops/mul.rs:22
+// Fallible reference calls return Result<_, fhe::Error>; here they throw fhe_b200::Error carrying
+// the fhe_b200_status code (same variants, see fhe_b200.h).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "fhe_b200.h"
+
+namespace fhe_b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int code) {
+  if (code != FHE_B200_OK) throw Error(code, fhe_b200_last_error());
+}
+
+namespace bfv {
+
+enum class Representation : int { PowerBasis = FHE_B200_POWER_BASIS, Ntt = FHE_B200_NTT };
+
+class BfvParameters {
+ public:
+  BfvParameters(const BfvParameters&) = delete;
+  BfvParameters& operator=(const BfvParameters&) = delete;
+  ~BfvParameters() { fhe_b200_params_destroy(h_); }
+  size_t degree() const { return fhe_b200_params_degree(h_); }
+  std::vector<uint64_t> moduli() const {
+    std::vector<uint64_t> m(fhe_b200_params_n_moduli(h_));
+    check(fhe_b200_params_moduli(h_, m.data()));
+    return m;
+  }
+  size_t max_level() const { return fhe_b200_params_n_moduli(h_) - 1; }
+  std::vector<uint64_t> mul_basis(uint32_t level) const {
+    uint32_t n = 0;
+    check(fhe_b200_params_mul_basis(h_, level, nullptr, &n));
+    std::vector<uint64_t> m(n);
+    check(fhe_b200_params_mul_basis(h_, level, m.data(), &n));
+    return m;
+  }
+  const fhe_b200_params* handle() const { return h_; }
+
+ private:
+  friend class BfvParametersBuilder;
+  explicit BfvParameters(fhe_b200_params* h) : h_(h) {}
+  fhe_b200_params* h_;
+};
+
+class BfvParametersBuilder {
+ public:
+  BfvParametersBuilder& set_degree(size_t d) { degree_ = (uint32_t)d; return *this; }
+  BfvParametersBuilder& set_plaintext_modulus(uint64_t t) { plaintext_ = t; return *this; }
+  BfvParametersBuilder& set_moduli(const std::vector<uint64_t>& m) { moduli_ = m; return *this; }
+  BfvParametersBuilder& set_moduli_sizes(const std::vector<uint32_t>& s) { sizes_ = s; return *this; }
+  BfvParametersBuilder& set_ntt_roots(const std::vector<uint64_t>& psi) { psi_ = psi; return *this; }
+  BfvParametersBuilder& set_device(int device) { device_ = device; return *this; }
+  // BfvParametersBuilder::build_arc (bfv/parameters.rs:555)
+  std::shared_ptr<BfvParameters> build_arc() const {
+    uint8_t pt[8];
+    for (int i = 0; i < 8; i++) pt[i] = (uint8_t)(plaintext_ >> (8 * i));
+    fhe_b200_params* h = nullptr;
+    if (!moduli_.empty() && !sizes_.empty())
+      throw Error(FHE_B200_INVALID_ARGUMENT, "ConflictingCiphertextModulusSpecifications");
+    if (!moduli_.empty())
+      check(fhe_b200_params_create(device_, degree_, moduli_.data(), (uint32_t)moduli_.size(), pt, 8,
+                                   psi_.empty() ? nullptr : psi_.data(), &h));
+    else
+      check(fhe_b200_params_create_from_sizes(device_, degree_, sizes_.data(), (uint32_t)sizes_.size(), pt, 8, &h));
+    return std::shared_ptr<BfvParameters>(new BfvParameters(h));
+  }
+
+ private:
+  uint32_t degree_ = 0;
+  uint64_t plaintext_ = 0;
+  std::vector<uint64_t> moduli_, psi_;
+  std::vector<uint32_t> sizes_;
+  int device_ = 0;
+};
+
+// A batch of `count` ciphertexts with `parts` polynomials each, at one level, resident in HBM.
+class Ciphertext {
+ public:
+  Ciphertext(std::shared_ptr<BfvParameters> par, uint32_t count, uint32_t parts = 2, uint32_t level = 0,
+             Representation r = Representation::Ntt, void* stream = nullptr)
+      : par_(std::move(par)), stream_(stream) {
+    check(fhe_b200_batch_alloc(par_->handle(), count, parts, level, (int)r, &h_));
+  }
+  Ciphertext(Ciphertext&& o) noexcept : par_(std::move(o.par_)), h_(o.h_), stream_(o.stream_) { o.h_ = nullptr; }
+  Ciphertext(const Ciphertext&) = delete;
+  ~Ciphertext() { fhe_b200_batch_free(h_); }
+
+  // host words [count][parts][limbs][N] == Vec<u64>::from(&Poly) per part (rq/convert.rs:474)
+  static Ciphertext from_host(std::shared_ptr<BfvParameters> par, const std::vector<uint64_t>& words, uint32_t count,
+                              uint32_t parts = 2, uint32_t level = 0, Representation r = Representation::Ntt) {
+    Ciphertext ct(std::move(par), count, parts, level, r);
+    if (words.size() != ct.words()) throw Error(FHE_B200_INVALID_ARGUMENT, "word count does not match the batch shape");
+    check(fhe_b200_batch_upload(ct.h_, 0, count, words.data(), ct.stream_));
+    check(fhe_b200_sync(ct.stream_));
+    return ct;
+  }
+  std::vector<uint64_t> to_host() const {
+    std::vector<uint64_t> w(words());
+    check(fhe_b200_batch_download(h_, 0, count(), w.data(), stream_));
+    return w;
+  }
+  uint32_t count() const { uint32_t c; check(fhe_b200_batch_info(h_, &c, nullptr, nullptr, nullptr, nullptr)); return c; }
+  uint32_t len() const { uint32_t p; check(fhe_b200_batch_info(h_, nullptr, &p, nullptr, nullptr, nullptr)); return p; }
+  uint32_t level() const { uint32_t l; check(fhe_b200_batch_info(h_, nullptr, nullptr, &l, nullptr, nullptr)); return l; }
+  uint32_t limbs() const { uint32_t l; check(fhe_b200_batch_info(h_, nullptr, nullptr, nullptr, &l, nullptr)); return l; }
+  size_t words() const { return (size_t)count() * len() * limbs() * par_->degree(); }
+
+  Ciphertext clone() const {
+    Ciphertext c(par_, count(), len(), level(), Representation::Ntt, stream_);
+    check(fhe_b200_batch_copy(c.h_, h_, stream_));
+    return c;
+  }
+  // bfv/ops/mod.rs:54, :148, :205
+  Ciphertext& operator+=(const Ciphertext& rhs) { check(fhe_b200_add(h_, rhs.h_, stream_)); return *this; }
+  Ciphertext& operator-=(const Ciphertext& rhs) { check(fhe_b200_sub(h_, rhs.h_, stream_)); return *this; }
+  Ciphertext operator-() const { Ciphertext c = clone(); check(fhe_b200_neg(c.h_, stream_)); return c; }
+  // &Ciphertext * &Ciphertext -> 3 parts (bfv/ops/mod.rs:259)
+  Ciphertext operator*(const Ciphertext& rhs) const {
+    Ciphertext out(par_, count(), 3, level(), Representation::Ntt, stream_);
+    check(fhe_b200_mul(h_, rhs.h_, out.h_, stream_));
+    return out;
+  }
+  // Ciphertext::switch_down (bfv/ciphertext.rs:148)
+  void switch_down() { check(fhe_b200_switch_down(h_, stream_)); }
+
+  fhe_b200_batch* handle() const { return h_; }
+  const std::shared_ptr<BfvParameters>& par() const { return par_; }
+  void* stream() const { return stream_; }
+
+ private:
+  std::shared_ptr<BfvParameters> par_;
+  fhe_b200_batch* h_ = nullptr;
+  void* stream_ = nullptr;
+};
+
+class KeySwitchingKey {
+ public:
+  // c0, c1: NTT-domain words [n_digits][ksk_limbs][N] of the key polynomials (key_switching_key.rs:22-45)
+  KeySwitchingKey(std::shared_ptr<BfvParameters> par, const std::vector<uint64_t>& c0, const std::vector<uint64_t>& c1,
+                  uint32_t n_digits, uint32_t ciphertext_level = 0, uint32_t ksk_level = 0)
+      : par_(std::move(par)), ciphertext_level_(ciphertext_level), ksk_level_(ksk_level) {
+    check(fhe_b200_ksk_upload(par_->handle(), ciphertext_level, ksk_level, c0.data(), c1.data(), n_digits, &h_));
+  }
+  KeySwitchingKey(const KeySwitchingKey&) = delete;
+  ~KeySwitchingKey() { fhe_b200_ksk_free(h_); }
+  const fhe_b200_ksk* handle() const { return h_; }
+  uint32_t ciphertext_level() const { return ciphertext_level_; }
+  const std::shared_ptr<BfvParameters>& par() const { return par_; }
+
+ private:
+  std::shared_ptr<BfvParameters> par_;
+  fhe_b200_ksk* h_ = nullptr;
+  uint32_t ciphertext_level_, ksk_level_;
+};
+
+class RelinearizationKey {
+ public:
+  explicit RelinearizationKey(std::shared_ptr<KeySwitchingKey> ksk) : ksk(std::move(ksk)) {}
+  // RelinearizationKey::relinearizes (relinearization_key.rs:70): (c0,c1,c2) -> (c0,c1)
+  Ciphertext relinearizes(const Ciphertext& ct) const {
+    Ciphertext out(ct.par(), ct.count(), 2, ct.level(), Representation::Ntt, ct.stream());
+    check(fhe_b200_relinearize(ct.handle(), ksk->handle(), out.handle(), ct.stream()));
+    return out;
+  }
+  std::shared_ptr<KeySwitchingKey> ksk;
+};
+
+class GaloisKey {
+ public:
+  GaloisKey(uint32_t exponent, std::shared_ptr<KeySwitchingKey> ksk) : exponent(exponent), ksk(std::move(ksk)) {}
+  // GaloisKey::relinearize (galois_key.rs:63)
+  Ciphertext relinearize(const Ciphertext& ct) const {
+    Ciphertext out(ct.par(), ct.count(), 2, ct.level(), Representation::Ntt, ct.stream());
+    check(fhe_b200_galois(ct.handle(), exponent, ksk->handle(), out.handle(), ct.stream()));
+    return out;
+  }
+  uint32_t exponent;
+  std::shared_ptr<KeySwitchingKey> ksk;
+};
+
+// rotation subset of EvaluationKey (evaluation_key.rs:110-170)
+class EvaluationKey {
+ public:
+  explicit EvaluationKey(std::shared_ptr<BfvParameters> par) : par_(std::move(par)) {}
+  void add_galois_key(std::shared_ptr<GaloisKey> gk) { gk_[gk->exponent % (2 * (uint32_t)par_->degree())] = std::move(gk); }
+  Ciphertext rotates_rows(const Ciphertext& ct) const { return at(2 * (uint32_t)par_->degree() - 1).relinearize(ct); }
+  Ciphertext rotates_columns_by(const Ciphertext& ct, uint32_t i) const {
+    uint64_t e = 1, m = 2 * par_->degree();
+    for (uint32_t k = 0; k < i; k++) e = e * 3 % m;  // evaluation_key.rs:278-286
+    return at((uint32_t)e).relinearize(ct);
+  }
+
+ private:
+  const GaloisKey& at(uint32_t e) const {
+    auto it = gk_.find(e);
+    if (it == gk_.end()) throw Error(FHE_B200_INVALID_ARGUMENT, "EvaluationKeyError: rotation not supported by this key");
+    return *it->second;
+  }
+  std::shared_ptr<BfvParameters> par_;
+  std::map<uint32_t, std::shared_ptr<GaloisKey>> gk_;
+};
+
+class Multiplicator {
+ public:
+  // Multiplicator::default (ops/mul.rs:101)
+  static Multiplicator default_(const RelinearizationKey& rk) { return Multiplicator(rk); }
+  // Multiplicator::enable_mod_switching (ops/mul.rs:155)
+  void enable_mod_switching() {
+    if (level_ >= rk_.ksk->par()->max_level()) throw Error(FHE_B200_NO_MORE_CONTEXT, "NoMoreContext");
+    mod_switch_ = true;
+  }
+  // Multiplicator::multiply (ops/mul.rs:165)
+  Ciphertext multiply(const Ciphertext& lhs, const Ciphertext& rhs) const {
+    if (lhs.level() != level_ || rhs.level() != level_) throw Error(FHE_B200_INVALID_LEVEL, "InvalidLevel");
+    Ciphertext out(lhs.par(), lhs.count(), 2, level_ + (mod_switch_ ? 1 : 0), Representation::Ntt, lhs.stream());
+    check(fhe_b200_mul_relin(lhs.handle(), rhs.handle(), rk_.ksk->handle(), mod_switch_ ? 1 : 0, out.handle(), lhs.stream()));
+    return out;
+  }
+
+ private:
+  explicit Multiplicator(const RelinearizationKey& rk) : rk_(rk), level_(rk.ksk->ciphertext_level()) {}
+  RelinearizationKey rk_;
+  uint32_t level_;
+  bool mod_switch_ = false;
+};
+
+}  // namespace bfv
+}  // namespace fhe_b200
