@@ -295,7 +295,7 @@ __global__ void switch_down_kernel(SwitchDownArgs A) {
     const LimbDev& M = A.limbs[A.ids[i]];
     u64 tmp = barrett64(xl, M.p, M.bhi, M.blo) + A.S.half_mod[i];   // :469
     u64 v = src[(size_t)i << A.logn] + 3 * M.p - tmp;              // :473
-    dst[(size_t)i << A.logn] = mul_shoup(v, A.S.inv[i], A.S.inv_s[i], M.p);  // :476
+    dst[(size_t)i << A.logn] = mul_shoup(v, A.S.inv[i], A.S.inv_s[i], M.p);  // :476 (always a Shoup pair)
   }
 }
 

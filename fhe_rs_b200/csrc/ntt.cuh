@@ -34,18 +34,25 @@ struct NttArgs {
   unsigned short ids[kMaxPos];  // limb position -> index into `limbs`
 };
 
-__device__ __forceinline__ void bf_fwd(u64& x, u64& y, u64 w, u64 ws, u64 p, u64 p2) {
+// x in [0,4p), 2p < 2^63: x - 2p is "negative" exactly when x < 2p
+__device__ __forceinline__ u64 csub2p(u64 x, u64 p2) {
+  u64 t = x - p2;
+  return (long long)t < 0 ? x : t;
+}
+template <bool SOL>
+__device__ __forceinline__ void bf_fwd(u64& x, u64& y, u64 w, u64 ws, u64 p, u64 p2, u32 c) {
   // ntt/native.rs:272-285
-  u64 X = csub(x, p2);
-  u64 T = mul_shoup_lazy(y, w, ws, p);
+  u64 X = csub2p(x, p2);
+  u64 T = mul_const_lazy<SOL>(y, w, ws, p, c);
   x = X + T;
   y = X + p2 - T;
 }
-__device__ __forceinline__ void bf_inv(u64& x, u64& y, u64 z, u64 zs, u64 p, u64 p2) {
+template <bool SOL>
+__device__ __forceinline__ void bf_inv(u64& x, u64& y, u64 z, u64 zs, u64 p, u64 p2, u32 c) {
   // ntt/native.rs:303-316
   u64 t = x;
-  x = csub(t + y, p2);
-  y = mul_shoup_lazy(p2 + t - y, z, zs, p);
+  x = csub2p(t + y, p2);
+  y = mul_const_lazy<SOL>(p2 + t - y, z, zs, p, c);
 }
 
 __device__ __forceinline__ u32 sm_phys(u32 i) { return i + (i >> 5); }
@@ -56,13 +63,14 @@ __device__ __forceinline__ u32 sm_phys(u32 i) { return i + (i >> 5); }
 // t: first local stage of this round (forward numbering).  s_base: global stage of
 // local stage 0.  root0: global block offset of this tile's transform at local stage 0
 // (0 for cols, matrix row index for rows; per batch lane for the rows layout).
-template <int LOGP, int LOGB, bool COLS, bool INV, int NS>
+template <int LOGP, int LOGB, bool COLS, bool INV, int NS, bool SOL>
 __device__ __forceinline__ void ntt_round(u64* sm, const LimbDev& L, int t, int s_base, u32 logn,
                                           u32 row0, bool first_global_pass) {
   constexpr int R = 1 << NS;
   constexpr u32 P = 1u << LOGP, B = 1u << LOGB;
   constexpr u32 G = (P * B) >> NS;
   const u64 p = L.p, p2 = L.p2;
+  const u32 c = (u32)L.sol_c;
   const int logstride = LOGP - t - NS;      // log2 of the in-group element stride
   for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
     u32 b, a_lo, a_hi;
@@ -97,7 +105,7 @@ __device__ __forceinline__ void ntt_round(u64* sm, const LimbDev& L, int t, int 
           if (jj & half) continue;
           u32 i_loc = (a_hi << u) + (jj >> (NS - u));
           u32 k = (1u << s) + (root0 << tl) + i_loc;   // omegas index m + i
-          bf_fwd(x[jj], x[jj + half], __ldg(L.om + k), __ldg(L.om_s + k), p, p2);
+          bf_fwd<SOL>(x[jj], x[jj + half], __ldg(L.om + k), __ldg(L.om_s + k), p, p2, c);
         }
       }
       if (s_base + t + NS == (int)logn) {  // last global stage: reduce3 (native.rs:238)
@@ -115,9 +123,9 @@ __device__ __forceinline__ void ntt_round(u64* sm, const LimbDev& L, int t, int 
 #pragma unroll
           for (int jj = 0; jj < R; jj++) {
             if (jj & half) continue;
-            u64 a = x[jj], c = x[jj + half];
-            x[jj] = mul_shoup(a + c, L.ninv, L.ninv_s, p);
-            x[jj + half] = mul_shoup(p2 + a - c, L.zn, L.zn_s, p);
+            u64 a = x[jj], b2 = x[jj + half];
+            x[jj] = csub(mul_const_lazy<SOL>(a + b2, L.ninv, L.ninv_s, p, c), p);
+            x[jj + half] = csub(mul_const_lazy<SOL>(p2 + a - b2, L.zn, L.zn_s, p, c), p);
           }
         } else {
 #pragma unroll
@@ -125,7 +133,7 @@ __device__ __forceinline__ void ntt_round(u64* sm, const LimbDev& L, int t, int 
             if (jj & half) continue;
             u32 i_loc = (a_hi << u) + (jj >> (NS - u));
             u32 k = (1u << logn) - (2u << s) + (root0 << tl) + i_loc;  // zetas_inv index N-2m+i
-            bf_inv(x[jj], x[jj + half], __ldg(L.zi + k), __ldg(L.zi_s + k), p, p2);
+            bf_inv<SOL>(x[jj], x[jj + half], __ldg(L.zi + k), __ldg(L.zi_s + k), p, p2, c);
           }
         }
       }
@@ -139,26 +147,33 @@ __device__ __forceinline__ void ntt_round(u64* sm, const LimbDev& L, int t, int 
   }
 }
 
-template <int LOGP, int LOGB, bool COLS, bool INV>
-__device__ __forceinline__ void ntt_tile_transform(u64* sm, const LimbDev& L, int s_base, u32 logn,
-                                                   u32 row0, bool first_pass) {
+template <int LOGP, int LOGB, bool COLS, bool INV, bool SOL>
+__device__ __forceinline__ void ntt_tile_transform_mode(u64* sm, const LimbDev& L, int s_base, u32 logn,
+                                                        u32 row0, bool first_pass) {
   constexpr int NR = (LOGP + 2) / 3;        // rounds
   constexpr int REM = LOGP - 3 * (NR - 1);  // stages in the short round (1..3)
   if (!INV) {
 #pragma unroll
     for (int r = 0; r < NR; r++) {
-      if (r < NR - 1) ntt_round<LOGP, LOGB, COLS, INV, 3>(sm, L, 3 * r, s_base, logn, row0, first_pass);
-      else ntt_round<LOGP, LOGB, COLS, INV, REM>(sm, L, 3 * r, s_base, logn, row0, first_pass);
+      if (r < NR - 1) ntt_round<LOGP, LOGB, COLS, INV, 3, SOL>(sm, L, 3 * r, s_base, logn, row0, first_pass);
+      else ntt_round<LOGP, LOGB, COLS, INV, REM, SOL>(sm, L, 3 * r, s_base, logn, row0, first_pass);
       __syncthreads();
     }
   } else {
 #pragma unroll
     for (int r = NR - 1; r >= 0; r--) {
-      if (r < NR - 1) ntt_round<LOGP, LOGB, COLS, INV, 3>(sm, L, 3 * r, s_base, logn, row0, first_pass);
-      else ntt_round<LOGP, LOGB, COLS, INV, REM>(sm, L, 3 * r, s_base, logn, row0, first_pass);
+      if (r < NR - 1) ntt_round<LOGP, LOGB, COLS, INV, 3, SOL>(sm, L, 3 * r, s_base, logn, row0, first_pass);
+      else ntt_round<LOGP, LOGB, COLS, INV, REM, SOL>(sm, L, 3 * r, s_base, logn, row0, first_pass);
       __syncthreads();
     }
   }
+}
+
+template <int LOGP, int LOGB, bool COLS, bool INV>
+__device__ __forceinline__ void ntt_tile_transform(u64* sm, const LimbDev& L, int s_base, u32 logn,
+                                                   u32 row0, bool first_pass) {
+  if (L.sol_c) ntt_tile_transform_mode<LOGP, LOGB, COLS, INV, true>(sm, L, s_base, logn, row0, first_pass);
+  else ntt_tile_transform_mode<LOGP, LOGB, COLS, INV, false>(sm, L, s_base, logn, row0, first_pass);
 }
 
 // cols kernel: tile = P=N1 points x C=2^LOGB adjacent columns.  grid.x = rows * (N2/C).

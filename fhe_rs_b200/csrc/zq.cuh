@@ -24,11 +24,12 @@ struct LimbDev {
   u64 zn;      // zetas_inv[N-2] * N^-1 mod p  (last inverse stage fused with the N^-1 scaling)
   u64 zn_s;    // shoup(zn)
   u64 c128;    // 2^128 mod p (folds the third accumulator word of lazy sums)
-  u64 pad;
+  u64 sol_c;   // 0: generic prime, constant multiplications use Shoup pairs (w, floor(w*2^64/p));
+               // c: p = 2^62 - c with c < 2^28 ("Solinas" limb): pairs are (w, w*2^32 mod p), see mul_const_lazy
   const u64* om;    // omegas[N]          = psi^{bitrev(i)}        (ntt/native.rs:50-56)
-  const u64* om_s;  // omegas_shoup[N]
+  const u64* om_s;  // companion word of omegas[i] (Shoup quotient or w*2^32 mod p)
   const u64* zi;    // zetas_inv[N]       = psi^{-(bitrev(i)+1)}
-  const u64* zi_s;  // zetas_inv_shoup[N]
+  const u64* zi_s;  // companion word of zetas_inv[i]
 };
 
 __device__ __forceinline__ u64 csub(u64 x, u64 p) { return x >= p ? x - p : x; }
@@ -40,6 +41,57 @@ __device__ __forceinline__ u64 mul_shoup_lazy(u64 a, u64 w, u64 ws, u64 p) {
 }
 __device__ __forceinline__ u64 mul_shoup(u64 a, u64 w, u64 ws, u64 p) {
   return csub(mul_shoup_lazy(a, w, ws, p), p);
+}
+
+// Multiplication of any 64-bit y by a precomputed constant w modulo p = 2^62 - c, c < 2^28,
+// result in [0,2p) -- the same contract as the reference's lazy_mul_shoup (zq/mod.rs:224), so it can
+// replace it inside the Harvey butterflies without changing any canonical output.
+//   y = y1*2^32 + y0 ;  w0 = w, w1 = w*2^32 mod p  (both < 2^62, precomputed)
+//   S = y0*w0 + y1*w1  (== y*w mod p, S < 2^95)   -- four 32x32->64 products, no 64x64 high product
+//   S = Shi*2^62 + Slo ;  2^62 == c (mod p)  =>  y*w == Shi*c + Slo < 2^33*2^28 + 2^62 < 2p
+// Five IMAD.WIDE against six IMAD.WIDE + four IMAD for the Shoup form; on B200 the FMA pipe
+// (IMAD 2 clk, IMAD.WIDE 3 clk per warp) is the binding resource of the NTT.
+__device__ __forceinline__ u64 mul_solinas_lazy(u64 y, u64 w0, u64 w1, u32 c) {
+  u64 r;
+  // P = y0*a0, Q = y1*b0 (low partial sums), M = y0*a1 + y1*b1 (< 2^63)
+  // H = M + (P >> 32) + (Q >> 32) + carry(lo32(P) + lo32(Q));  S = H*2^32 + s0
+  // Shi = H >> 30 (33 bits: h + t*2^32), Slo = (H & (2^30-1))*2^32 + s0;  r = Shi*c + Slo
+  asm("{\n\t"
+      ".reg .u32 y0, y1, a0, a1, b0, b1, pl, ph, ql, qh, m0, m1, s0, h0, h1, hh, tt, sl, r0, r1;\n\t"
+      ".reg .u64 P, Q, M, S, R;\n\t"
+      "mov.b64 {y0, y1}, %1;\n\t"
+      "mov.b64 {a0, a1}, %2;\n\t"
+      "mov.b64 {b0, b1}, %3;\n\t"
+      "mul.wide.u32 P, y0, a0;\n\t"
+      "mul.wide.u32 Q, y1, b0;\n\t"
+      "mul.wide.u32 M, y0, a1;\n\t"
+      "mad.wide.u32 M, y1, b1, M;\n\t"
+      "mov.b64 {pl, ph}, P;\n\t"
+      "mov.b64 {ql, qh}, Q;\n\t"
+      "mov.b64 {m0, m1}, M;\n\t"
+      "add.cc.u32 s0, pl, ql;\n\t"
+      "addc.cc.u32 h0, ph, qh;\n\t"
+      "addc.u32 h1, m1, 0;\n\t"
+      "add.cc.u32 h0, h0, m0;\n\t"
+      "addc.u32 h1, h1, 0;\n\t"
+      "shf.r.wrap.b32 hh, h0, h1, 30;\n\t"
+      "shr.u32 tt, h1, 30;\n\t"
+      "and.b32 sl, h0, 0x3fffffff;\n\t"
+      "mov.b64 S, {s0, sl};\n\t"
+      "mad.wide.u32 R, hh, %4, S;\n\t"
+      "mov.b64 {r0, r1}, R;\n\t"
+      "mad.lo.u32 r1, tt, %4, r1;\n\t"
+      "mov.b64 %0, {r0, r1};\n\t"
+      "}"
+      : "=l"(r)
+      : "l"(y), "l"(w0), "l"(w1), "r"(c));
+  return r;
+}
+
+// lazy product by a precomputed constant pair (a, b) in the limb's mode
+template <bool SOL>
+__device__ __forceinline__ u64 mul_const_lazy(u64 y, u64 a, u64 b, u64 p, u32 c) {
+  return SOL ? mul_solinas_lazy(y, a, b, c) : mul_shoup_lazy(y, a, b, p);
 }
 
 // device shoup(a) = floor(a * 2^64 / p), a < p (zq/mod.rs:195).  Uses the Barrett
