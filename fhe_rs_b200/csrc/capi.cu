@@ -368,23 +368,19 @@ static int params_build(int device, uint32_t degree, const std::vector<u64>& mod
     // limb mode: p = 2^62 - c with c < 2^28 takes the Solinas constant-multiplication form
     const u64 cc = (1ull << 62) - q;
     const bool sol = (q >> 61) == 1 && cc < (1ull << 28) && !getenv("FHE_B200_NO_SOLINAS");
-    if (sol) {
-      auto comp = [&](const std::vector<u64>& v) {
-        std::vector<u64> o(v.size());
-        for (size_t k = 0; k < v.size(); k++) o[k] = (u64)((((u128)v[k]) << 32) % q);
-        return o;
-      };
-      d.sol_c = cc;
-      d.ninv_s = (u64)((((u128)t.ninv) << 32) % q);
-      d.zn_s = (u64)((((u128)t.zn) << 32) % q);
-      d.om = p->to_dev(t.om); d.om_s = p->to_dev(comp(t.om));
-      d.zi = p->to_dev(t.zi); d.zi_s = p->to_dev(comp(t.zi));
-    } else {
-      d.sol_c = 0;
-      d.ninv_s = t.ninv_s; d.zn_s = t.zn_s;
-      d.om = p->to_dev(t.om); d.om_s = p->to_dev(t.om_s);
-      d.zi = p->to_dev(t.zi); d.zi_s = p->to_dev(t.zi_s);
-    }
+    auto pairs = [&](const std::vector<u64>& v, const std::vector<u64>& shoup) {
+      std::vector<ulonglong2> o(v.size());
+      for (size_t k = 0; k < v.size(); k++) {
+        o[k].x = v[k];
+        o[k].y = sol ? (u64)((((u128)v[k]) << 32) % q) : shoup[k];
+      }
+      return o;
+    };
+    d.sol_c = sol ? cc : 0;
+    d.ninv_s = sol ? (u64)((((u128)t.ninv) << 32) % q) : t.ninv_s;
+    d.zn_s = sol ? (u64)((((u128)t.zn) << 32) % q) : t.zn_s;
+    d.om = p->to_dev(pairs(t.om, t.om_s));
+    d.zi = p->to_dev(pairs(t.zi, t.zi_s));
     p->h_limbs.push_back(d);
   }
   p->d_limbs = p->to_dev(p->h_limbs);

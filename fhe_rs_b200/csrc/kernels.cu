@@ -70,10 +70,13 @@ __global__ void tensor_kernel(TensorArgs A) {
     a0 = A.xa[o + c]; a1 = A.xa[o + ((size_t)A.E << A.logn) + c];
     b0 = A.xb[o + c]; b1 = A.xb[o + ((size_t)A.E << A.logn) + c];
   }
-  u64 c0 = mulmod(a0, b0, M.p, M.bhi, M.blo);
-  u64 c2 = mulmod(a1, b1, M.p, M.bhi, M.blo);
-  u128 s = (u128)a0 * b1 + (u128)a1 * b0;  // < 2^125
-  u64 c1 = barrett128((u64)s, (u64)(s >> 64), M.p, M.bhi, M.blo);
+  u64 c0 = mulmod_limb(a0, b0, M);
+  u64 c2 = mulmod_limb(a1, b1, M);
+  Acc192 s;                                 // a0*b1 + a1*b0 < 2^125, one reduction
+  s.clear();
+  s.mac(a0, b1);
+  s.mac(a1, b0);
+  u64 c1 = s.reduce(M);
   size_t o = (((size_t)ct * 3) * K + pos) << A.logn;
   A.out[o + c] = c0;
   A.out[o + ((size_t)K << A.logn) + c] = c1;

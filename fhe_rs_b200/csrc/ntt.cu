@@ -1,6 +1,9 @@
 // NTT launcher: picks the (N1, N2) split and tile shapes for a given N and instantiates
 // the tile kernels of ntt.cuh.
+#include <cstdlib>
+
 #include "engine.hpp"
+#include "ntt_fast.cuh"
 
 namespace fhe_b200 {
 
@@ -26,6 +29,30 @@ void run_cols(const NttArgs& a, cudaStream_t st) {
   const size_t smem = (T + (T >> 5) + 1) * sizeof(u64);
   ntt_cols_kernel<LOGP, LOGB, INV><<<a.n_rows * tiles, 256, smem, st>>>(a);
   g_launches++;
+}
+
+template <int LOGP, bool COLS, bool INV>
+void run_fast(const NttArgs& a, cudaStream_t st) {
+  constexpr size_t smem = 2 * (4096 + 128) * sizeof(u64);
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaFuncSetAttribute(ntt_fast_kernel<LOGP, COLS, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  constexpr int LOGB = 12 - LOGP;
+  const u32 tiles = COLS ? ((1u << (a.logn - LOGP)) >> LOGB) : ((1u << a.logn1) >> LOGB);
+  ntt_fast_kernel<LOGP, COLS, INV><<<a.n_rows * tiles, 512, smem, st>>>(a);
+  g_launches++;
+}
+template <bool INV>
+void run_fast_cols_for(const NttArgs& a, cudaStream_t st) {
+  switch (a.logn1) {
+    case 7: run_fast<7, true, INV>(a, st); break;
+    case 8: run_fast<8, true, INV>(a, st); break;
+    case 9: run_fast<9, true, INV>(a, st); break;
+    case 10: run_fast<10, true, INV>(a, st); break;
+    default: break;
+  }
 }
 
 template <bool INV>
@@ -81,12 +108,23 @@ void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const Li
   second.in = out;
   second.in_div = 1;
   second.reduce_on_load = 0;
+  static const bool generic = getenv("FHE_B200_GENERIC_NTT") != nullptr;
+  if (generic) {
+    if (!inverse) {
+      run_cols_for<false>(a, st);
+      run_rows<6, 6, false>(second, st);
+    } else {
+      run_rows<6, 6, true>(a, st);
+      run_cols_for<true>(second, st);
+    }
+    return;
+  }
   if (!inverse) {
-    run_cols_for<false>(a, st);
-    run_rows<6, 6, false>(second, st);
+    run_fast_cols_for<false>(a, st);
+    run_fast<6, false, false>(second, st);
   } else {
-    run_rows<6, 6, true>(a, st);
-    run_cols_for<true>(second, st);
+    run_fast<6, false, true>(a, st);
+    run_fast_cols_for<true>(second, st);
   }
 }
 

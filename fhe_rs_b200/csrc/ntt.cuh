@@ -105,7 +105,8 @@ __device__ __forceinline__ void ntt_round(u64* sm, const LimbDev& L, int t, int 
           if (jj & half) continue;
           u32 i_loc = (a_hi << u) + (jj >> (NS - u));
           u32 k = (1u << s) + (root0 << tl) + i_loc;   // omegas index m + i
-          bf_fwd<SOL>(x[jj], x[jj + half], __ldg(L.om + k), __ldg(L.om_s + k), p, p2, c);
+          const ulonglong2 w = __ldg(L.om + k);
+          bf_fwd<SOL>(x[jj], x[jj + half], w.x, w.y, p, p2, c);
         }
       }
       if (s_base + t + NS == (int)logn) {  // last global stage: reduce3 (native.rs:238)
@@ -133,7 +134,8 @@ __device__ __forceinline__ void ntt_round(u64* sm, const LimbDev& L, int t, int 
             if (jj & half) continue;
             u32 i_loc = (a_hi << u) + (jj >> (NS - u));
             u32 k = (1u << logn) - (2u << s) + (root0 << tl) + i_loc;  // zetas_inv index N-2m+i
-            bf_inv<SOL>(x[jj], x[jj + half], __ldg(L.zi + k), __ldg(L.zi_s + k), p, p2, c);
+            const ulonglong2 z = __ldg(L.zi + k);
+            bf_inv<SOL>(x[jj], x[jj + half], z.x, z.y, p, p2, c);
           }
         }
       }

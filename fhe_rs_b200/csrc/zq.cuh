@@ -26,10 +26,9 @@ struct LimbDev {
   u64 c128;    // 2^128 mod p (folds the third accumulator word of lazy sums)
   u64 sol_c;   // 0: generic prime, constant multiplications use Shoup pairs (w, floor(w*2^64/p));
                // c: p = 2^62 - c with c < 2^28 ("Solinas" limb): pairs are (w, w*2^32 mod p), see mul_const_lazy
-  const u64* om;    // omegas[N]          = psi^{bitrev(i)}        (ntt/native.rs:50-56)
-  const u64* om_s;  // companion word of omegas[i] (Shoup quotient or w*2^32 mod p)
-  const u64* zi;    // zetas_inv[N]       = psi^{-(bitrev(i)+1)}
-  const u64* zi_s;  // companion word of zetas_inv[i]
+  // twiddle tables as (value, companion) pairs so one 128-bit load fetches both words:
+  const ulonglong2* om;  // omegas[N]    = psi^{bitrev(i)}       (ntt/native.rs:50-56) + Shoup quotient | w*2^32 mod p
+  const ulonglong2* zi;  // zetas_inv[N] = psi^{-(bitrev(i)+1)}  + companion
 };
 
 __device__ __forceinline__ u64 csub(u64 x, u64 p) { return x >= p ? x - p : x; }
@@ -138,34 +137,94 @@ __device__ __forceinline__ u64 mulmod(u64 a, u64 b, u64 p, u64 bhi, u64 blo) {
   return barrett128(a * b, __umul64hi(a, b), p, bhi, blo);
 }
 
-// 192-bit lazy accumulator for sums of 64x64 products (used by the RNS scaler and the
+// Full 128-bit product of two operands < 2^62 (four IMAD.WIDE; the middle sum a0*b1 + a1*b0 < 2^63
+// cannot overflow because both high words are < 2^30).
+__device__ __forceinline__ void mul128_62(u64 a, u64 b, u64& lo, u64& hi) {
+  asm("{\n\t"
+      ".reg .u32 a0, a1, b0, b1, p0, p1, m0, m1, q0, q1, t1, t2, t3;\n\t"
+      ".reg .u64 P, M, Q;\n\t"
+      "mov.b64 {a0, a1}, %2;\n\t"
+      "mov.b64 {b0, b1}, %3;\n\t"
+      "mul.wide.u32 P, a0, b0;\n\t"
+      "mul.wide.u32 M, a0, b1;\n\t"
+      "mad.wide.u32 M, a1, b0, M;\n\t"
+      "mul.wide.u32 Q, a1, b1;\n\t"
+      "mov.b64 {p0, p1}, P;\n\t"
+      "mov.b64 {m0, m1}, M;\n\t"
+      "mov.b64 {q0, q1}, Q;\n\t"
+      "add.cc.u32 t1, p1, m0;\n\t"
+      "addc.cc.u32 t2, q0, m1;\n\t"
+      "addc.u32 t3, q1, 0;\n\t"
+      "mov.b64 %0, {p0, t1};\n\t"
+      "mov.b64 %1, {t2, t3};\n\t"
+      "}"
+      : "=l"(lo), "=l"(hi)
+      : "l"(a), "l"(b));
+}
+
+// Reduction of a lazy sum V = hi*2^128 + mid*2^64 + lo (hi < 2^32) modulo p = 2^62 - c, c < 2^28, to [0,2p):
+// three folds of 2^62 == c (mod p).
+__device__ __forceinline__ u64 fold192_solinas(u64 lo, u64 mid, u64 hi, u32 c) {
+  typedef unsigned __int128 u128;
+  // fold 1: V1 = V >> 62 (up to 98 bits: v1a low 64, v1b high), V0 = V & (2^62-1)
+  const u64 mask = (1ull << 62) - 1;
+  u64 v0 = lo & mask;
+  u64 v1a = (lo >> 62) | (mid << 2);
+  u64 v1b = (mid >> 62) | (hi << 2);                 // < 2^34
+  // U = V1*c + V0  (< 2^98*2^28 ... bounded by the caller: V < 2^160 is never reached; here V < 2^131 => V1 < 2^69)
+  u128 U = (u128)v1a * c + v0;
+  U += ((u128)(v1b * (u64)c)) << 64;                 // v1b*c < 2^62
+  // fold 2: U < 2^98  =>  U1 = U >> 62 < 2^36
+  u64 ulo = (u64)U, uhi = (u64)(U >> 64);
+  u64 u0 = ulo & mask;
+  u64 u1 = (ulo >> 62) | (uhi << 2);                 // < 2^36
+  u128 R = (u128)u1 * c + u0;                        // < 2^64 + 2^62
+  // fold 3
+  u64 rlo = (u64)R, rhi = (u64)(R >> 64);
+  u64 r1 = (rlo >> 62) | (rhi << 2);                 // < 2^3
+  return r1 * c + (rlo & mask);                      // < 2^31 + 2^62 < 2p
+}
+
+// 192-bit lazy accumulator for sums of products of operands < 2^62 (used by the RNS scaler and the
 // key-switch inner product; replaces the reference's per-term Shoup reduction,
 // rns/scaler.rs:340-347 and rq/ops.rs:208, with one reduction at the end).
 struct Acc192 {
   u64 lo, mid, hi;
   __device__ __forceinline__ void clear() { lo = mid = hi = 0; }
-  __device__ __forceinline__ void mac(u64 a, u64 b) {
-    u64 pl = a * b, ph = __umul64hi(a, b);
-    lo += pl;
-    u64 c = lo < pl;
-    mid += c;
-    hi += mid < c;
-    mid += ph;
-    hi += mid < ph;
+  __device__ __forceinline__ void mac(u64 a, u64 b) {  // a, b < 2^62
+    u64 pl, ph;
+    mul128_62(a, b, pl, ph);
+    asm("add.cc.u64 %0, %0, %3;\n\t"
+        "addc.cc.u64 %1, %1, %4;\n\t"
+        "addc.u64 %2, %2, 0;"
+        : "+l"(lo), "+l"(mid), "+l"(hi)
+        : "l"(pl), "l"(ph));
   }
   __device__ __forceinline__ void add64(u64 v) {
-    lo += v;
-    u64 c = lo < v;
-    mid += c;
-    hi += mid < c;
+    asm("add.cc.u64 %0, %0, %3;\n\t"
+        "addc.cc.u64 %1, %1, 0;\n\t"
+        "addc.u64 %2, %2, 0;"
+        : "+l"(lo), "+l"(mid), "+l"(hi)
+        : "l"(v));
   }
   // canonical residue of the accumulated value; hi must be < 2^32
   __device__ __forceinline__ u64 reduce(const LimbDev& m) const {
+    if (m.sol_c) return csub(fold192_solinas(lo, mid, hi, (u32)m.sol_c), m.p);
     u64 r1 = barrett128_lazy(lo, mid, m.p, m.bhi, m.blo);  // [0,2p)
     u64 hl = hi * m.c128, hh = __umul64hi(hi, m.c128);
     u64 r2 = barrett128_lazy(hl, hh, m.p, m.bhi, m.blo);   // [0,2p)
     return csub(csub(r1 + r2, m.p2), m.p);
   }
 };
+
+// canonical a*b mod p for canonical a, b (Modulus::mul / mul_opt, zq/mod.rs:131-156)
+__device__ __forceinline__ u64 mulmod_limb(u64 a, u64 b, const LimbDev& m) {
+  if (m.sol_c) {
+    u64 lo, hi;
+    mul128_62(a, b, lo, hi);
+    return csub(fold192_solinas(lo, hi, 0, (u32)m.sol_c), m.p);
+  }
+  return mulmod(a, b, m.p, m.bhi, m.blo);
+}
 
 }  // namespace fhe_b200

@@ -1,0 +1,37 @@
+"""Small driver for ncu captures: runs the hot path once (or a selected primitive) at the north-star size.
+    python profiles/probe.py ntt|mulrelin [count]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import fhe_rs_b200 as F
+from bench import fill_uniform, DEGREE, N_MODULI, PLAINTEXT
+
+what = sys.argv[1] if len(sys.argv) > 1 else "mulrelin"
+count = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+par = F.BfvParameters(DEGREE, PLAINTEXT, moduli_sizes=[62] * N_MODULI, device=0)
+moduli = par.moduli()
+A = F.Ciphertext(par, count, 2)
+fill_uniform(torch, A, moduli, 1)
+if what == "ntt":
+    for _ in range(2):
+        A.into_power_basis()
+        A.into_ntt()
+else:
+    B = F.Ciphertext(par, count, 2)
+    fill_uniform(torch, B, moduli, 2)
+    rng = np.random.default_rng(7)
+    kc = np.zeros((2, N_MODULI, N_MODULI, DEGREE), np.uint64)
+    for i, q in enumerate(moduli):
+        kc[:, :, i, :] = rng.integers(0, q, size=(2, N_MODULI, DEGREE), dtype=np.uint64)
+    rk = F.RelinearizationKey.from_arrays(par, kc[0], kc[1])
+    m = F.Multiplicator.default(rk)
+    for _ in range(2):
+        out = m.multiply(A, B)
+    out.sync()
+torch.cuda.synchronize()
+print("probe done", what, count)
