@@ -92,133 +92,264 @@ struct ScaleArgs {
   u32 polys, out_rows_per_poly, start, n_out, split3, logn;
 };
 
+// 256-bit two's-complement helpers on 4 x u64 (stand-in for ethnum::U256 wrapping arithmetic)
 struct U256 {
   u64 w0, w1, w2, w3;
 };
-__device__ __forceinline__ void u256_addmul(U256& s, u64 r, u64 lo, u64 hi, bool negate) {
-  // s +/-= r * (hi:lo)   (192-bit product, wrapping 256-bit accumulate; rns/scaler.rs:260-298)
-  u128 p0 = (u128)r * lo, p1 = (u128)r * hi;
-  u64 a0 = (u64)p0;
-  u128 mid = (p0 >> 64) + (u64)p1;
-  u64 a1 = (u64)mid;
-  u128 top = (mid >> 64) + (p1 >> 64);
-  u64 a2 = (u64)top, a3 = (u64)(top >> 64);
-  if (negate) {  // two's complement of the 256-bit product
-    a0 = ~a0; a1 = ~a1; a2 = ~a2; a3 = ~a3;
-    u128 c = (u128)a0 + 1; a0 = (u64)c;
-    c = (u128)a1 + (u64)(c >> 64); a1 = (u64)c;
-    c = (u128)a2 + (u64)(c >> 64); a2 = (u64)c;
-    a3 += (u64)(c >> 64);
-  }
-  u128 c = (u128)s.w0 + a0; s.w0 = (u64)c;
-  c = (u128)s.w1 + a1 + (u64)(c >> 64); s.w1 = (u64)c;
-  c = (u128)s.w2 + a2 + (u64)(c >> 64); s.w2 = (u64)c;
-  s.w3 = s.w3 + a3 + (u64)(c >> 64);
+__device__ __forceinline__ U256 u256_from_acc(const u32 (&a)[7]) {
+  U256 r;
+  r.w0 = ((u64)a[1] << 32) | a[0];
+  r.w1 = ((u64)a[3] << 32) | a[2];
+  r.w2 = ((u64)a[5] << 32) | a[4];
+  r.w3 = a[6];
+  return r;
+}
+__device__ __forceinline__ U256 u256_add(U256 a, U256 b) {
+  U256 r;
+  asm("add.cc.u64 %0, %4, %8;\n\t"
+      "addc.cc.u64 %1, %5, %9;\n\t"
+      "addc.cc.u64 %2, %6, %10;\n\t"
+      "addc.u64 %3, %7, %11;"
+      : "=l"(r.w0), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3)
+      : "l"(a.w0), "l"(a.w1), "l"(a.w2), "l"(a.w3), "l"(b.w0), "l"(b.w1), "l"(b.w2), "l"(b.w3));
+  return r;
+}
+__device__ __forceinline__ U256 u256_sub(U256 a, U256 b) {
+  U256 r;
+  asm("sub.cc.u64 %0, %4, %8;\n\t"
+      "subc.cc.u64 %1, %5, %9;\n\t"
+      "subc.cc.u64 %2, %6, %10;\n\t"
+      "subc.u64 %3, %7, %11;"
+      : "=l"(r.w0), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3)
+      : "l"(a.w0), "l"(a.w1), "l"(a.w2), "l"(a.w3), "l"(b.w0), "l"(b.w1), "l"(b.w2), "l"(b.w3));
+  return r;
+}
+// (128-bit v) * (128-bit theta) mod 2^256
+__device__ __forceinline__ U256 u256_mul_128(u128 v, u64 tlo, u64 thi) {
+  u32 a[7] = {0, 0, 0, 0, 0, 0, 0}, b[7] = {0, 0, 0, 0, 0, 0, 0};
+  mac_theta(a, (u64)v, tlo, thi);
+  mac_theta(b, (u64)(v >> 64), tlo, thi);
+  U256 lo = u256_from_acc(a), hi = u256_from_acc(b);
+  U256 hs = {0, hi.w0, hi.w1, hi.w2};
+  return u256_add(lo, hs);
 }
 
-// One thread per (poly, coefficient): RnsScaler::scale (rns/scaler.rs:249-352) on the column
-// of n_from residues, writing n_out residues.  NF = compile-time bound on n_from.
-template <int NF>
-__global__ void scale_kernel(ScaleArgs A) {
-  extern __shared__ u64 smem[];
+// RnsScaler::scale (rns/scaler.rs:249-352) for a tile of TC = 64 coefficient columns of one polynomial.
+// 256 threads = 64 columns x 4 groups.  The n_from source residues of the tile are staged in shared
+// memory once; the fixed-point sums (v, w) are computed exactly as coded in the reference, split four
+// ways over the source limbs and recombined; the n_out output limbs are then produced four at a time
+// per thread (four independent lazy accumulators), so the register footprint stays small and eight
+// CTAs fit per SM -- the one-thread-per-column form was latency bound at 3 warps per scheduler.
+constexpr int kScaleTC = 64;
+
+struct ScaleSmem {
+  u64* r;       // [n_from][TC]
+  u64* omega;   // [n_from][n_out4]   (transposed: four outputs per pair of 128-bit loads)
+  u64* gamma;   // [n_out4]
+  u64 *tgl, *tgh, *tol, *toh, *tos;   // theta tables [n_from]
+  u32* part;    // [3][4][7][TC] partial fixed-point sums
+  u64* vw;      // [4][TC]: v.lo, v.hi, w.lo, w.hi
+  u32* wsign;   // [TC]
+};
+
+__global__ void __launch_bounds__(256) scale_kernel(ScaleArgs A) {
+  extern __shared__ __align__(16) u64 smem[];
   const ScalerDev& S = A.S;
   const u32 nf = S.n_from, n_out = A.n_out;
-  u64* s_omega = smem;                        // [n_out][nf]
-  u64* s_gamma = s_omega + (size_t)n_out * nf;  // [n_out]
-  u64* s_tgl = s_gamma + n_out;               // theta_garner lo/hi [nf]
-  u64* s_tgh = s_tgl + nf;
-  u64* s_tol = s_tgh + nf;                    // theta_omega lo/hi/sign [nf]
-  u64* s_toh = s_tol + nf;
-  u64* s_tos = s_toh + nf;
-  for (u32 i = threadIdx.x; i < n_out * nf; i += blockDim.x)
-    s_omega[i] = S.omega[(size_t)(A.start + i / nf) * nf + i % nf];
-  for (u32 i = threadIdx.x; i < n_out; i += blockDim.x) s_gamma[i] = S.gamma[A.start + i];
-  for (u32 i = threadIdx.x; i < nf; i += blockDim.x) {
-    s_tgl[i] = S.tgar_lo[i];
-    s_tgh[i] = S.tgar_hi[i];
-    s_tol[i] = S.to_lo[i];
-    s_toh[i] = S.to_hi[i];
-    s_tos[i] = S.to_sign[i];
+  const u32 n_out4 = (n_out + 3) & ~3u;
+  constexpr u32 TC = kScaleTC;
+  ScaleSmem sm;
+  sm.r = smem;
+  sm.omega = sm.r + (size_t)nf * TC;
+  sm.gamma = sm.omega + (size_t)nf * n_out4;
+  sm.tgl = sm.gamma + n_out4;
+  sm.tgh = sm.tgl + nf;
+  sm.tol = sm.tgh + nf;
+  sm.toh = sm.tol + nf;
+  sm.tos = sm.toh + nf;
+  sm.vw = sm.tos + nf;
+  sm.part = reinterpret_cast<u32*>(sm.vw + 4 * TC);
+  sm.wsign = sm.part + 3 * 4 * 7 * TC;
+
+  const u32 N = 1u << A.logn;
+  const u32 per_poly = N / TC;
+  const u32 poly = blockIdx.x / per_poly;
+  const u32 c0 = (blockIdx.x % per_poly) * TC;
+  const u64* src = A.in + (((size_t)poly * nf) << A.logn) + c0;
+  const u32 tid = threadIdx.x, cc = tid & (TC - 1), g = tid / TC;
+
+  for (u32 i = tid; i < nf * TC; i += 256) sm.r[i] = src[((size_t)(i / TC) << A.logn) + (i % TC)];
+  for (u32 i = tid; i < nf * n_out4; i += 256) {
+    u32 ii = i / n_out4, jj = i % n_out4;
+    sm.omega[i] = jj < n_out ? S.omega[(size_t)(A.start + jj) * nf + ii] : 0;
+  }
+  for (u32 i = tid; i < n_out4; i += 256) sm.gamma[i] = i < n_out ? S.gamma[A.start + i] : 0;
+  for (u32 i = tid; i < nf; i += 256) {
+    sm.tgl[i] = S.tgar_lo[i];
+    sm.tgh[i] = S.tgar_hi[i];
+    sm.tol[i] = S.to_lo[i];
+    sm.toh[i] = S.to_hi[i];
+    sm.tos[i] = S.to_sign[i];
   }
   __syncthreads();
 
-  const u32 N = 1u << A.logn;
-  const u32 per_poly = N / blockDim.x;
-  const u32 poly = blockIdx.x / per_poly;
-  const u32 c = (blockIdx.x % per_poly) * blockDim.x + threadIdx.x;
-  const u64* src = A.in + (((size_t)poly * nf) << A.logn) + c;
-
-  u64 r[NF];
-#pragma unroll
-  for (int i = 0; i < NF; i++) r[i] = (u32)i < nf ? src[(size_t)i << A.logn] : 0;
-
-  // v = round(sum_i r_i * theta_garner_i / 2^shift)   (:260-272)
-  U256 sg = {0, 0, 0, 0};
-#pragma unroll
-  for (int i = 0; i < NF; i++)
-    if ((u32)i < nf) u256_addmul(sg, r[i], s_tgl[i], s_tgh[i], false);
-  u128 v;
+  // ---- fixed-point sums, source limbs i = g, g+4, ...   (:260-268, :279-292)
   {
-    // theta_garner_shift is in [123,127] for moduli < 2^62 and <= 64 limbs (rns/scaler.rs:130-142),
-    // so shift-1 = 64 + bs with 58 <= bs <= 62
-    const u32 bs = S.shift - 1 - 64;
-    u64 lo = (sg.w1 >> bs) | (sg.w2 << (64 - bs));
-    u64 hi = (sg.w2 >> bs) | (sg.w3 << (64 - bs));
-    u128 x = ((u128)hi << 64) | lo;
-    v = (x >> 1) + (x & 1);
+    u32 av[7] = {0, 0, 0, 0, 0, 0, 0}, ap[7] = {0, 0, 0, 0, 0, 0, 0}, an[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (u32 i = g; i < nf; i += 4) {
+      const u64 r = sm.r[i * TC + cc];
+      mac_theta(av, r, sm.tgl[i], sm.tgh[i]);
+      if (!S.is_one) {
+        if (sm.tos[i]) mac_theta(an, r, sm.tol[i], sm.toh[i]);   // table-driven, warp-uniform branch
+        else mac_theta(ap, r, sm.tol[i], sm.toh[i]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      sm.part[((0 * 4 + g) * 7 + k) * TC + cc] = av[k];
+      sm.part[((1 * 4 + g) * 7 + k) * TC + cc] = ap[k];
+      sm.part[((2 * 4 + g) * 7 + k) * TC + cc] = an[k];
+    }
   }
+  __syncthreads();
+  if (g == 0) {
+    U256 sum[3];
+#pragma unroll
+    for (int w = 0; w < 3; w++) {
+      U256 acc = {0, 0, 0, 0};
+#pragma unroll
+      for (int gg = 0; gg < 4; gg++) {
+        u32 a[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) a[k] = sm.part[((w * 4 + gg) * 7 + k) * TC + cc];
+        acc = u256_add(acc, u256_from_acc(a));
+      }
+      sum[w] = acc;
+    }
+    // v = round(sum / 2^shift)  (:270-272).  theta_garner_shift is in [123,127] for moduli < 2^62 and <= 64
+    // limbs (:130-142), so shift-1 = 64 + bs with 58 <= bs <= 62
+    const u32 bs = S.shift - 1 - 64;
+    u64 lo = (sum[0].w1 >> bs) | (sum[0].w2 << (64 - bs));
+    u64 hi = (sum[0].w2 >> bs) | (sum[0].w3 << (64 - bs));
+    u128 x = ((u128)hi << 64) | lo;
+    u128 v = (x >> 1) + (x & 1);
+    // w = round((sum_i +/- r_i * theta_omega_i -/+ v * theta_gamma) / 2^127)   (:294-314)
+    bool w_sign = false;
+    u128 w = 0;
+    if (!S.is_one) {
+      U256 so = u256_sub(sum[1], sum[2]);
+      U256 vt = u256_mul_128(v, S.tg_lo, S.tg_hi);
+      so = S.tg_sign ? u256_add(so, vt) : u256_sub(so, vt);
+      w_sign = (so.w3 != 0) || (so.w2 >> 63);
+      if (w_sign) {
+        u64 n1 = ~so.w1, n2 = ~so.w2, n3 = ~so.w3;
+        u128 y = ((u128)((n2 >> 62) | (n3 << 2)) << 64) | ((n1 >> 62) | (n2 << 2));
+        w = (y + 1) >> 1;
+      } else {
+        u128 y = ((u128)((so.w2 >> 62) | (so.w3 << 2)) << 64) | ((so.w1 >> 62) | (so.w2 << 2));
+        w = (y >> 1) + (y & 1);
+      }
+    }
+    sm.vw[0 * TC + cc] = (u64)v;
+    sm.vw[1 * TC + cc] = (u64)(v >> 64);
+    sm.vw[2 * TC + cc] = (u64)w;
+    sm.vw[3 * TC + cc] = (u64)(w >> 64);
+    sm.wsign[cc] = w_sign;
+  }
+  __syncthreads();
 
-  // w = round((sum_i +/- r_i * theta_omega_i -/+ v * theta_gamma) / 2^127)   (:276-314)
+  // ---- outputs (:316-351): y_j = (-(v mod q_j) * gamma_j +/- w + sum_i r_i * omega_ji) mod q_j
+  const u64 v_lo = sm.vw[0 * TC + cc], v_hi = sm.vw[1 * TC + cc];
+  const u64 w_lo = sm.vw[2 * TC + cc], w_hi = sm.vw[3 * TC + cc];
+  const bool w_sign = sm.wsign[cc] != 0;
+  for (u32 j0 = g * 4; j0 < n_out; j0 += 16) {
+    Acc192 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc[k].clear();
+    const ulonglong2* om = reinterpret_cast<const ulonglong2*>(sm.omega + j0);
+#pragma unroll 2
+    for (u32 i = 0; i < nf; i++) {
+      const u64 r = sm.r[i * TC + cc];
+      const ulonglong2 o0 = om[(size_t)i * (n_out4 / 2)], o1 = om[(size_t)i * (n_out4 / 2) + 1];
+      acc[0].mac(r, o0.x);
+      acc[1].mac(r, o0.y);
+      acc[2].mac(r, o1.x);
+      acc[3].mac(r, o1.y);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 jj = j0 + k;
+      if (jj >= n_out) break;
+      const LimbDev& M = A.limbs[S.to_ids[A.start + jj]];
+      u64 vr = reduce128_limb(v_lo, v_hi, M);
+      acc[k].mac(vr ? M.p - vr : 0, sm.gamma[jj]);
+      if (!S.is_one) {
+        u64 wr = reduce128_limb(w_lo, w_hi, M);
+        acc[k].add64(w_sign ? (wr ? M.p - wr : 0) : wr);
+      }
+      u64 y = acc[k].reduce(M);
+      u64* dst;
+      if (A.split3) {
+        u32 ct = poly / 3, part = poly % 3;
+        dst = part < 2 ? A.out0 + ((((size_t)ct * 2 + part) * n_out + jj) << A.logn)
+                       : A.out1 + (((size_t)ct * n_out + jj) << A.logn);
+      } else {
+        dst = A.out0 + (((size_t)poly * A.out_rows_per_poly + jj) << A.logn);
+      }
+      dst[c0 + cc] = y;
+    }
+  }
+}
+
+// fallback for rings smaller than one tile (N < 64): one thread per coefficient, same arithmetic
+__global__ void scale_small_kernel(ScaleArgs A) {
+  const ScalerDev& S = A.S;
+  const u32 nf = S.n_from, n_out = A.n_out;
+  const u32 N = 1u << A.logn;
+  const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= A.polys * N) return;
+  const u32 poly = idx >> A.logn, c = idx & (N - 1);
+  const u64* src = A.in + (((size_t)poly * nf) << A.logn) + c;
+  u32 av[7] = {0, 0, 0, 0, 0, 0, 0}, ap[7] = {0, 0, 0, 0, 0, 0, 0}, an[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (u32 i = 0; i < nf; i++) {
+    const u64 r = src[(size_t)i << A.logn];
+    mac_theta(av, r, S.tgar_lo[i], S.tgar_hi[i]);
+    if (!S.is_one) {
+      if (S.to_sign[i]) mac_theta(an, r, S.to_lo[i], S.to_hi[i]);
+      else mac_theta(ap, r, S.to_lo[i], S.to_hi[i]);
+    }
+  }
+  U256 sg = u256_from_acc(av);
+  const u32 bs = S.shift - 1 - 64;
+  u64 lo = (sg.w1 >> bs) | (sg.w2 << (64 - bs));
+  u64 hi = (sg.w2 >> bs) | (sg.w3 << (64 - bs));
+  u128 x = ((u128)hi << 64) | lo;
+  u128 v = (x >> 1) + (x & 1);
   bool w_sign = false;
   u128 w = 0;
   if (!S.is_one) {
-    U256 so = {0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < NF; i++)
-      if ((u32)i < nf) u256_addmul(so, r[i], s_tol[i], s_toh[i], s_tos[i] != 0);
-    // v * theta_gamma (128 x 128 -> 256), subtracted unless theta_gamma_sign
-    u256_addmul(so, (u64)v, S.tg_lo, S.tg_hi, !S.tg_sign);
-    {
-      // high half: (v >> 64) * theta_gamma << 64
-      U256 t = {0, 0, 0, 0};
-      u256_addmul(t, (u64)(v >> 64), S.tg_lo, S.tg_hi, false);
-      U256 sh = {0, t.w0, t.w1, t.w2};
-      if (!S.tg_sign) {  // negate
-        sh.w0 = ~sh.w0; sh.w1 = ~sh.w1; sh.w2 = ~sh.w2; sh.w3 = ~sh.w3;
-        u128 cc = (u128)sh.w0 + 1; sh.w0 = (u64)cc;
-        cc = (u128)sh.w1 + (u64)(cc >> 64); sh.w1 = (u64)cc;
-        cc = (u128)sh.w2 + (u64)(cc >> 64); sh.w2 = (u64)cc;
-        sh.w3 += (u64)(cc >> 64);
-      }
-      u128 cc = (u128)so.w0 + sh.w0; so.w0 = (u64)cc;
-      cc = (u128)so.w1 + sh.w1 + (u64)(cc >> 64); so.w1 = (u64)cc;
-      cc = (u128)so.w2 + sh.w2 + (u64)(cc >> 64); so.w2 = (u64)cc;
-      so.w3 = so.w3 + sh.w3 + (u64)(cc >> 64);
-    }
+    U256 so = u256_sub(u256_from_acc(ap), u256_from_acc(an));
+    U256 vt = u256_mul_128(v, S.tg_lo, S.tg_hi);
+    so = S.tg_sign ? u256_add(so, vt) : u256_sub(so, vt);
     w_sign = (so.w3 != 0) || (so.w2 >> 63);
     if (w_sign) {
       u64 n1 = ~so.w1, n2 = ~so.w2, n3 = ~so.w3;
-      u128 x = ((u128)((n2 >> 62) | (n3 << 2)) << 64) | ((n1 >> 62) | (n2 << 2));
-      w = (x + 1) >> 1;
+      u128 y = ((u128)((n2 >> 62) | (n3 << 2)) << 64) | ((n1 >> 62) | (n2 << 2));
+      w = (y + 1) >> 1;
     } else {
-      u128 x = ((u128)((so.w2 >> 62) | (so.w3 << 2)) << 64) | ((so.w1 >> 62) | (so.w2 << 2));
-      w = (x >> 1) + (x & 1);
+      u128 y = ((u128)((so.w2 >> 62) | (so.w3 << 2)) << 64) | ((so.w1 >> 62) | (so.w2 << 2));
+      w = (y >> 1) + (y & 1);
     }
   }
-
-  // outputs (:316-351): y_j = (-(v mod q_j) * gamma_j +/- w + sum_i r_i * omega_ji) mod q_j
   for (u32 j = 0; j < n_out; j++) {
     const LimbDev& M = A.limbs[S.to_ids[A.start + j]];
     Acc192 acc;
     acc.clear();
-    const u64* om = s_omega + (size_t)j * nf;
-#pragma unroll
-    for (int i = 0; i < NF; i++)
-      if ((u32)i < nf) acc.mac(r[i], om[i]);
-    u64 vr = barrett128((u64)v, (u64)(v >> 64), M.p, M.bhi, M.blo);
-    acc.mac(vr ? M.p - vr : 0, s_gamma[j]);
+    for (u32 i = 0; i < nf; i++) acc.mac(src[(size_t)i << A.logn], S.omega[(size_t)(A.start + j) * nf + i]);
+    u64 vr = reduce128_limb((u64)v, (u64)(v >> 64), M);
+    acc.mac(vr ? M.p - vr : 0, S.gamma[A.start + j]);
     if (!S.is_one) {
-      u64 wr = barrett128((u64)w, (u64)(w >> 64), M.p, M.bhi, M.blo);
+      u64 wr = reduce128_limb((u64)w, (u64)(w >> 64), M);
       acc.add64(w_sign ? (wr ? M.p - wr : 0) : wr);
     }
     u64 y = acc.reduce(M);
@@ -348,14 +479,21 @@ void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* 
   A.polys = polys; A.out_rows_per_poly = out_rows_per_poly; A.start = start; A.n_out = n_out;
   A.split3 = split3; A.logn = logn;
   const u32 N = 1u << logn;
-  const u32 threads = N < 128 ? N : 128;
-  const unsigned blocks = polys * (N / threads);
-  const size_t smem = ((size_t)n_out * S.n_from + n_out + 5 * (size_t)S.n_from) * sizeof(u64);
-  if (S.n_from <= 4) scale_kernel<4><<<blocks, threads, smem, st>>>(A);
-  else if (S.n_from <= 8) scale_kernel<8><<<blocks, threads, smem, st>>>(A);
-  else if (S.n_from <= 16) scale_kernel<16><<<blocks, threads, smem, st>>>(A);
-  else if (S.n_from <= 32) scale_kernel<32><<<blocks, threads, smem, st>>>(A);
-  else scale_kernel<64><<<blocks, threads, smem, st>>>(A);
+  if (N < (u32)kScaleTC) {
+    const u32 total = polys * N;
+    scale_small_kernel<<<(total + 63) / 64, 64, 0, st>>>(A);
+    g_launches++;
+    return;
+  }
+  const size_t n_out4 = (n_out + 3) & ~(size_t)3, nf = S.n_from;
+  const size_t smem = (nf * kScaleTC + nf * n_out4 + n_out4 + 5 * nf + 4 * kScaleTC) * sizeof(u64) +
+                      (3 * 4 * 7 * kScaleTC + kScaleTC) * sizeof(u32);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  scale_kernel<<<polys * (N / kScaleTC), 256, smem, st>>>(A);
   g_launches++;
 }
 

@@ -39,19 +39,28 @@ __device__ __forceinline__ u64 csub2p(u64 x, u64 p2) {
   u64 t = x - p2;
   return (long long)t < 0 ? x : t;
 }
+// Forward butterfly (ntt/native.rs:272-285).
+//  generic limb : the reference's ranges -- x, y in [0,4p), X = x - 2p*[x >= 2p], T in [0,2p).
+//  Solinas limb : any 64-bit x, y; X = x - 2p*[x >= 2^63] in [0, 2^63+2c), T < 2^62+2^61, so
+//                 X + T < 2^64 and X + 2p - T in [0, 2^64): same residues, cheaper range control.
 template <bool SOL>
 __device__ __forceinline__ void bf_fwd(u64& x, u64& y, u64 w, u64 ws, u64 p, u64 p2, u32 c) {
-  // ntt/native.rs:272-285
-  u64 X = csub2p(x, p2);
+  u64 X = SOL ? fold63_solinas(x, 2 * c) : csub2p(x, p2);
   u64 T = mul_const_lazy<SOL>(y, w, ws, p, c);
   x = X + T;
   y = X + p2 - T;
 }
+// canonical residue of a forward-transform output
+template <bool SOL>
+__device__ __forceinline__ u64 fwd_final(u64 v, u64 p, u64 p2, u32 c) {
+  if (SOL) v = fold63_solinas(v, 2 * c);  // < 2^63 + 2c = 2p + 4c
+  return csub(csub2p(v, p2), p);           // native.rs:238 reduce3
+}
+// Inverse butterfly (ntt/native.rs:303-316): x, y in [0,2p) in and out.
 template <bool SOL>
 __device__ __forceinline__ void bf_inv(u64& x, u64& y, u64 z, u64 zs, u64 p, u64 p2, u32 c) {
-  // ntt/native.rs:303-316
   u64 t = x;
-  x = csub2p(t + y, p2);
+  x = SOL ? addback2p(t + y - p2, p2) : csub2p(t + y, p2);
   y = mul_const_lazy<SOL>(p2 + t - y, z, zs, p, c);
 }
 
@@ -111,7 +120,7 @@ __device__ __forceinline__ void ntt_round(u64* sm, const LimbDev& L, int t, int 
       }
       if (s_base + t + NS == (int)logn) {  // last global stage: reduce3 (native.rs:238)
 #pragma unroll
-        for (int j = 0; j < R; j++) x[j] = csub(csub(x[j], p2), p);
+        for (int j = 0; j < R; j++) x[j] = fwd_final<SOL>(x[j], p, p2, c);
       }
     } else {
 #pragma unroll

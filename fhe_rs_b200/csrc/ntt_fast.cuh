@@ -83,7 +83,7 @@ struct FastTile {
         }
         if (s_base + t + NS == (int)logn) {
 #pragma unroll
-          for (int j = 0; j < R; j++) v[j] = csub(csub2p(v[j], p2), p);
+          for (int j = 0; j < R; j++) v[j] = fwd_final<SOL>(v[j], p, p2, c);
         }
       } else {
 #pragma unroll
@@ -164,10 +164,43 @@ struct FastTile {
     }
   }
 
+  // The rows layout (one contiguous 4096-word chunk) reaches its unit-stride round with 8 consecutive
+  // words per thread: touching global memory directly there costs 32 sectors per request (ncu
+  // ntt_r2: 14.7 sectors/request, lg_throttle).  That end of the pass is therefore staged through
+  // shared memory with fully coalesced 128-bit global accesses; every other global access pattern
+  // (64-byte segments) stays register-direct.
+  static __device__ __forceinline__ void stage_in(const u64* __restrict__ src, u64* buf, bool reduce_on_load,
+                                                  const LimbDev& L) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = (k * 512 + threadIdx.x) * 2;
+      ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + i);
+      if (reduce_on_load) {
+        v.x = barrett64(v.x, L.p, L.bhi, L.blo);
+        v.y = barrett64(v.y, L.p, L.bhi, L.blo);
+      }
+      const u32 ph = sm_phys(i);
+      buf[ph] = v.x;
+      buf[ph + 1] = v.y;
+    }
+  }
+  static __device__ __forceinline__ void stage_out(u64* __restrict__ dst, const u64* buf) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = (k * 512 + threadIdx.x) * 2;
+      const u32 ph = sm_phys(i);
+      ulonglong2 v;
+      v.x = buf[ph];
+      v.y = buf[ph + 1];
+      *reinterpret_cast<ulonglong2*>(dst + i) = v;
+    }
+  }
+
   static __device__ __forceinline__ void run(const u64* src, u64* dst, u32 gstride_a, u64* sm, bool reduce_on_load,
                                              const LimbDev& L, int s_base, u32 logn, u32 row0, bool first_pass) {
     u64 x[8];
     u64* buf[2] = {sm, sm + TW};
+    constexpr bool STAGE = !COLS;  // stage the unit-stride end of a rows pass
     if (!INV) {
 #pragma unroll
       for (int r = 0; r < NR; r++) {
@@ -176,18 +209,23 @@ struct FastTile {
         if (r < NR - 1)
           round<3>(x, r, src, dst, gstride_a, in, out, r == 0, false, reduce_on_load, L, s_base, logn, row0, first_pass);
         else
-          round<REM>(x, r, src, dst, gstride_a, in, out, r == 0, true, reduce_on_load, L, s_base, logn, row0, first_pass);
-        if (r < NR - 1) __syncthreads();
+          round<REM>(x, r, src, dst, gstride_a, in, out, r == 0, !STAGE, reduce_on_load, L, s_base, logn, row0, first_pass);
+        if (r < NR - 1 || STAGE) __syncthreads();
       }
+      if (STAGE) stage_out(dst, buf[(NR - 1) & 1]);
     } else {
+      if (STAGE) {
+        stage_in(src, buf[NR & 1], reduce_on_load, L);  // the buffer round NR-1 reads from
+        __syncthreads();
+      }
 #pragma unroll
       for (int r = NR - 1; r >= 0; r--) {
         u64* in = buf[(r + 1) & 1];
         u64* out = buf[r & 1];
         if (r < NR - 1)
-          round<3>(x, r, src, dst, gstride_a, in, out, r == NR - 1, r == 0, reduce_on_load, L, s_base, logn, row0, first_pass);
+          round<3>(x, r, src, dst, gstride_a, in, out, false, r == 0, reduce_on_load, L, s_base, logn, row0, first_pass);
         else
-          round<REM>(x, r, src, dst, gstride_a, in, out, true, r == 0, reduce_on_load, L, s_base, logn, row0, first_pass);
+          round<REM>(x, r, src, dst, gstride_a, in, out, !STAGE, r == 0, reduce_on_load, L, s_base, logn, row0, first_pass);
         if (r > 0) __syncthreads();
       }
     }

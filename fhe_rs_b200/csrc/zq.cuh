@@ -52,9 +52,47 @@ __device__ __forceinline__ u64 mul_shoup(u64 a, u64 w, u64 ws, u64 p) {
 // (IMAD 2 clk, IMAD.WIDE 3 clk per warp) is the binding resource of the NTT.
 __device__ __forceinline__ u64 mul_solinas_lazy(u64 y, u64 w0, u64 w1, u32 c) {
   u64 r;
-  // P = y0*a0, Q = y1*b0 (low partial sums), M = y0*a1 + y1*b1 (< 2^63)
-  // H = M + (P >> 32) + (Q >> 32) + carry(lo32(P) + lo32(Q));  S = H*2^32 + s0
-  // Shi = H >> 30 (33 bits: h + t*2^32), Slo = (H & (2^30-1))*2^32 + s0;  r = Shi*c + Slo
+  // two word-serial 32x64 products (the high IMAD.WIDE takes the low one's top word as addend, so the
+  // FMA pipe does those additions), one 96-bit addition, one fold:
+  //   y0*w0 = PH*2^32 + p0 ,  y1*w1 = QH*2^32 + q0 ,  S = (PH + QH + carry(p0+q0))*2^32 + (p0+q0 mod 2^32)
+  //   H = S >> 32 < 2^63 ;  Shi = H >> 30 = hh + tt*2^32 ;  Slo = (H mod 2^30)*2^32 + s0 ;  r = Shi*c + Slo
+  asm("{\n\t"
+      ".reg .u32 y0, y1, a0, a1, b0, b1, p0, pc, q0, qc, s0, h0, h1, hh, tt, sl, r0, r1;\n\t"
+      ".reg .u64 P, Q, PH, QH, PC, QC, S, R;\n\t"
+      "mov.b64 {y0, y1}, %1;\n\t"
+      "mov.b64 {a0, a1}, %2;\n\t"
+      "mov.b64 {b0, b1}, %3;\n\t"
+      "mul.wide.u32 P, y0, a0;\n\t"
+      "mul.wide.u32 Q, y1, b0;\n\t"
+      "mov.b64 {p0, pc}, P;\n\t"
+      "mov.b64 {q0, qc}, Q;\n\t"
+      "cvt.u64.u32 PC, pc;\n\t"
+      "cvt.u64.u32 QC, qc;\n\t"
+      "mad.wide.u32 PH, y0, a1, PC;\n\t"
+      "mad.wide.u32 QH, y1, b1, QC;\n\t"
+      "add.cc.u32 s0, p0, q0;\n\t"
+      "mov.b64 {h0, h1}, PH;\n\t"
+      "mov.b64 {r0, r1}, QH;\n\t"
+      "addc.cc.u32 h0, h0, r0;\n\t"
+      "addc.u32 h1, h1, r1;\n\t"
+      "shf.r.wrap.b32 hh, h0, h1, 30;\n\t"
+      "shr.u32 tt, h1, 30;\n\t"
+      "and.b32 sl, h0, 0x3fffffff;\n\t"
+      "mov.b64 S, {s0, sl};\n\t"
+      "mad.wide.u32 R, hh, %4, S;\n\t"
+      "mov.b64 {r0, r1}, R;\n\t"
+      "mad.lo.u32 r1, tt, %4, r1;\n\t"
+      "mov.b64 %0, {r0, r1};\n\t"
+      "}"
+      : "=l"(r)
+      : "l"(y), "l"(w0), "l"(w1), "r"(c));
+  return r;
+}
+
+// alternative instruction selection of the same product (kept for bench_micro/bf_bench.cu): four plain
+// products, M = y0*a1 + y1*b1 accumulated by the FMA pipe, five carry adds
+__device__ __forceinline__ u64 mul_solinas_lazy_v1(u64 y, u64 w0, u64 w1, u32 c) {
+  u64 r;
   asm("{\n\t"
       ".reg .u32 y0, y1, a0, a1, b0, b1, pl, ph, ql, qh, m0, m1, s0, h0, h1, hh, tt, sl, r0, r1;\n\t"
       ".reg .u64 P, Q, M, S, R;\n\t"
@@ -84,6 +122,42 @@ __device__ __forceinline__ u64 mul_solinas_lazy(u64 y, u64 w0, u64 w1, u32 c) {
       "}"
       : "=l"(r)
       : "l"(y), "l"(w0), "l"(w1), "r"(c));
+  return r;
+}
+
+// x (any 64-bit value) -> x - 2p*[x >= 2^63]  in [0, 2^63 + 2c), using 2^64 - 2p = 2^63 + 2c:
+// clear bit 63 and add bit63 * 2c (one IMAD.WIDE instead of compare + select on the busy ALU pipe)
+__device__ __forceinline__ u64 fold63_solinas(u64 x, u32 c2) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 lo, hi, b;\n\t"
+      ".reg .u64 M;\n\t"
+      "mov.b64 {lo, hi}, %1;\n\t"
+      "shr.u32 b, hi, 31;\n\t"
+      "and.b32 hi, hi, 0x7fffffff;\n\t"
+      "mov.b64 M, {lo, hi};\n\t"
+      "mad.wide.u32 %0, b, %2, M;\n\t"
+      "}"
+      : "=l"(r)
+      : "l"(x), "r"(c2));
+  return r;
+}
+// t in (-2p, 2p) as two's complement -> t + 2p*[t < 0]  (conditional add-back on the FMA pipe)
+__device__ __forceinline__ u64 addback2p(u64 t, u64 p2) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 lo, hi, b, pl, ph;\n\t"
+      ".reg .u64 R;\n\t"
+      "mov.b64 {lo, hi}, %1;\n\t"
+      "mov.b64 {pl, ph}, %2;\n\t"
+      "shr.u32 b, hi, 31;\n\t"
+      "mad.wide.u32 R, b, pl, %1;\n\t"
+      "mov.b64 {lo, hi}, R;\n\t"
+      "mad.lo.u32 hi, b, ph, hi;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t"
+      "}"
+      : "=l"(r)
+      : "l"(t), "l"(p2));
   return r;
 }
 
@@ -216,6 +290,65 @@ struct Acc192 {
     return csub(csub(r1 + r2, m.p2), m.p);
   }
 };
+
+// canonical residue of a 128-bit value
+__device__ __forceinline__ u64 reduce128_limb(u64 lo, u64 hi, const LimbDev& m) {
+  if (m.sol_c) return csub(fold192_solinas(lo, hi, 0, (u32)m.sol_c), m.p);
+  return barrett128(lo, hi, m.p, m.bhi, m.blo);
+}
+
+// acc (7 x 32-bit words, little endian) += r * theta, r = r1*2^32 + r0 (any 64-bit), theta = 128-bit
+// (t3:t2:t1:t0).  Two word-serial 32x128 products (IMAD.WIDE with the running carry as addend:
+// 32x32 + 32 < 2^64, no overflow) added at word offsets 0 and 1.  Used for the fixed-point sums of
+// RnsScaler::scale (rns/scaler.rs:260-298), whose U256 accumulator never exceeds 2^200 here.
+__device__ __forceinline__ void mac_theta(u32 (&a)[7], u64 r, u64 tlo, u64 thi) {
+  asm("{\n\t"
+      ".reg .u32 r0, r1, t0, t1, t2, t3, u0, u1, u2, u3, u4, c;\n\t"
+      ".reg .u64 P, C;\n\t"
+      "mov.b64 {r0, r1}, %7;\n\t"
+      "mov.b64 {t0, t1}, %8;\n\t"
+      "mov.b64 {t2, t3}, %9;\n\t"
+      // U = r0 * theta
+      "mul.wide.u32 P, r0, t0;\n\t"
+      "mov.b64 {u0, c}, P;\n\t"
+      "cvt.u64.u32 C, c;\n\t"
+      "mad.wide.u32 P, r0, t1, C;\n\t"
+      "mov.b64 {u1, c}, P;\n\t"
+      "cvt.u64.u32 C, c;\n\t"
+      "mad.wide.u32 P, r0, t2, C;\n\t"
+      "mov.b64 {u2, c}, P;\n\t"
+      "cvt.u64.u32 C, c;\n\t"
+      "mad.wide.u32 P, r0, t3, C;\n\t"
+      "mov.b64 {u3, u4}, P;\n\t"
+      "add.cc.u32 %0, %0, u0;\n\t"
+      "addc.cc.u32 %1, %1, u1;\n\t"
+      "addc.cc.u32 %2, %2, u2;\n\t"
+      "addc.cc.u32 %3, %3, u3;\n\t"
+      "addc.cc.u32 %4, %4, u4;\n\t"
+      "addc.cc.u32 %5, %5, 0;\n\t"
+      "addc.u32 %6, %6, 0;\n\t"
+      // V = r1 * theta, one word up
+      "mul.wide.u32 P, r1, t0;\n\t"
+      "mov.b64 {u0, c}, P;\n\t"
+      "cvt.u64.u32 C, c;\n\t"
+      "mad.wide.u32 P, r1, t1, C;\n\t"
+      "mov.b64 {u1, c}, P;\n\t"
+      "cvt.u64.u32 C, c;\n\t"
+      "mad.wide.u32 P, r1, t2, C;\n\t"
+      "mov.b64 {u2, c}, P;\n\t"
+      "cvt.u64.u32 C, c;\n\t"
+      "mad.wide.u32 P, r1, t3, C;\n\t"
+      "mov.b64 {u3, u4}, P;\n\t"
+      "add.cc.u32 %1, %1, u0;\n\t"
+      "addc.cc.u32 %2, %2, u1;\n\t"
+      "addc.cc.u32 %3, %3, u2;\n\t"
+      "addc.cc.u32 %4, %4, u3;\n\t"
+      "addc.cc.u32 %5, %5, u4;\n\t"
+      "addc.u32 %6, %6, 0;\n\t"
+      "}"
+      : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6])
+      : "l"(r), "l"(tlo), "l"(thi));
+}
 
 // canonical a*b mod p for canonical a, b (Modulus::mul / mul_opt, zq/mod.rs:131-156)
 __device__ __forceinline__ u64 mulmod_limb(u64 a, u64 b, const LimbDev& m) {
