@@ -134,142 +134,97 @@ __device__ __forceinline__ U256 u256_mul_128(u128 v, u64 tlo, u64 thi) {
   return u256_add(lo, hs);
 }
 
-// RnsScaler::scale (rns/scaler.rs:249-352) for a tile of TC = 64 coefficient columns of one polynomial.
-// 256 threads = 64 columns x 4 groups.  The n_from source residues of the tile are staged in shared
-// memory once; the fixed-point sums (v, w) are computed exactly as coded in the reference, split four
-// ways over the source limbs and recombined; the n_out output limbs are then produced four at a time
-// per thread (four independent lazy accumulators), so the register footprint stays small and eight
-// CTAs fit per SM -- the one-thread-per-column form was latency bound at 3 warps per scheduler.
-constexpr int kScaleTC = 64;
+// RnsScaler::scale (rns/scaler.rs:249-352): one thread per coefficient column, 128 columns per CTA.
+// The n_from source residues of the tile are staged in shared memory (coalesced load, conflict-free
+// reads) so the thread keeps only accumulators in registers; the fixed-point sums (v, w) are computed
+// exactly as coded in the reference; the output limbs are produced four at a time (four independent
+// lazy accumulators per thread give the instruction-level parallelism the single dependent carry
+// chain lacks -- ncu: the register-resident one-limb-at-a-time form ran at 0.3 IPC).
+constexpr int kScaleTC = 128;
 
-struct ScaleSmem {
-  u64* r;       // [n_from][TC]
-  u64* omega;   // [n_from][n_out4]   (transposed: four outputs per pair of 128-bit loads)
-  u64* gamma;   // [n_out4]
-  u64 *tgl, *tgh, *tol, *toh, *tos;   // theta tables [n_from]
-  u32* part;    // [3][4][7][TC] partial fixed-point sums
-  u64* vw;      // [4][TC]: v.lo, v.hi, w.lo, w.hi
-  u32* wsign;   // [TC]
-};
-
-__global__ void __launch_bounds__(256) scale_kernel(ScaleArgs A) {
+__global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   extern __shared__ __align__(16) u64 smem[];
   const ScalerDev& S = A.S;
   const u32 nf = S.n_from, n_out = A.n_out;
   const u32 n_out4 = (n_out + 3) & ~3u;
   constexpr u32 TC = kScaleTC;
-  ScaleSmem sm;
-  sm.r = smem;
-  sm.omega = sm.r + (size_t)nf * TC;
-  sm.gamma = sm.omega + (size_t)nf * n_out4;
-  sm.tgl = sm.gamma + n_out4;
-  sm.tgh = sm.tgl + nf;
-  sm.tol = sm.tgh + nf;
-  sm.toh = sm.tol + nf;
-  sm.tos = sm.toh + nf;
-  sm.vw = sm.tos + nf;
-  sm.part = reinterpret_cast<u32*>(sm.vw + 4 * TC);
-  sm.wsign = sm.part + 3 * 4 * 7 * TC;
+  u64* s_r = smem;                                // [n_from][TC]
+  u64* s_omega = s_r + (size_t)nf * TC;           // [n_from][n_out4]  (transposed)
+  u64* s_gamma = s_omega + (size_t)nf * n_out4;   // [n_out4]
+  u64* s_tgl = s_gamma + n_out4;                  // theta tables [n_from]
+  u64* s_tgh = s_tgl + nf;
+  u64* s_tol = s_tgh + nf;
+  u64* s_toh = s_tol + nf;
+  u64* s_tos = s_toh + nf;
 
   const u32 N = 1u << A.logn;
   const u32 per_poly = N / TC;
   const u32 poly = blockIdx.x / per_poly;
   const u32 c0 = (blockIdx.x % per_poly) * TC;
   const u64* src = A.in + (((size_t)poly * nf) << A.logn) + c0;
-  const u32 tid = threadIdx.x, cc = tid & (TC - 1), g = tid / TC;
+  const u32 cc = threadIdx.x;
 
-  for (u32 i = tid; i < nf * TC; i += 256) sm.r[i] = src[((size_t)(i / TC) << A.logn) + (i % TC)];
-  for (u32 i = tid; i < nf * n_out4; i += 256) {
-    u32 ii = i / n_out4, jj = i % n_out4;
-    sm.omega[i] = jj < n_out ? S.omega[(size_t)(A.start + jj) * nf + ii] : 0;
-  }
-  for (u32 i = tid; i < n_out4; i += 256) sm.gamma[i] = i < n_out ? S.gamma[A.start + i] : 0;
-  for (u32 i = tid; i < nf; i += 256) {
-    sm.tgl[i] = S.tgar_lo[i];
-    sm.tgh[i] = S.tgar_hi[i];
-    sm.tol[i] = S.to_lo[i];
-    sm.toh[i] = S.to_hi[i];
-    sm.tos[i] = S.to_sign[i];
+  for (u32 i = 0; i < nf; i++) s_r[i * TC + cc] = src[((size_t)i << A.logn) + cc];
+  for (u32 jj = 0; jj < n_out4; jj++)
+    for (u32 ii = cc; ii < nf; ii += TC)
+      s_omega[ii * n_out4 + jj] = jj < n_out ? S.omega[(size_t)(A.start + jj) * nf + ii] : 0;
+  for (u32 i = cc; i < n_out4; i += TC) s_gamma[i] = i < n_out ? S.gamma[A.start + i] : 0;
+  for (u32 i = cc; i < nf; i += TC) {
+    s_tgl[i] = S.tgar_lo[i];
+    s_tgh[i] = S.tgar_hi[i];
+    s_tol[i] = S.to_lo[i];
+    s_toh[i] = S.to_hi[i];
+    s_tos[i] = S.to_sign[i];
   }
   __syncthreads();
 
-  // ---- fixed-point sums, source limbs i = g, g+4, ...   (:260-268, :279-292)
+  // v = round(sum_i r_i * theta_garner_i / 2^shift)   (:260-272)
+  u128 v;
   {
-    u32 av[7] = {0, 0, 0, 0, 0, 0, 0}, ap[7] = {0, 0, 0, 0, 0, 0, 0}, an[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (u32 i = g; i < nf; i += 4) {
-      const u64 r = sm.r[i * TC + cc];
-      mac_theta(av, r, sm.tgl[i], sm.tgh[i]);
-      if (!S.is_one) {
-        if (sm.tos[i]) mac_theta(an, r, sm.tol[i], sm.toh[i]);   // table-driven, warp-uniform branch
-        else mac_theta(ap, r, sm.tol[i], sm.toh[i]);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 7; k++) {
-      sm.part[((0 * 4 + g) * 7 + k) * TC + cc] = av[k];
-      sm.part[((1 * 4 + g) * 7 + k) * TC + cc] = ap[k];
-      sm.part[((2 * 4 + g) * 7 + k) * TC + cc] = an[k];
-    }
-  }
-  __syncthreads();
-  if (g == 0) {
-    U256 sum[3];
-#pragma unroll
-    for (int w = 0; w < 3; w++) {
-      U256 acc = {0, 0, 0, 0};
-#pragma unroll
-      for (int gg = 0; gg < 4; gg++) {
-        u32 a[7];
-#pragma unroll
-        for (int k = 0; k < 7; k++) a[k] = sm.part[((w * 4 + gg) * 7 + k) * TC + cc];
-        acc = u256_add(acc, u256_from_acc(a));
-      }
-      sum[w] = acc;
-    }
-    // v = round(sum / 2^shift)  (:270-272).  theta_garner_shift is in [123,127] for moduli < 2^62 and <= 64
-    // limbs (:130-142), so shift-1 = 64 + bs with 58 <= bs <= 62
+    u32 acc[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+    for (u32 i = 0; i < nf; i++) mac_theta(acc, s_r[i * TC + cc], s_tgl[i], s_tgh[i]);
+    U256 sg = u256_from_acc(acc);
+    // theta_garner_shift is in [123,127] for moduli < 2^62 and <= 64 limbs (:130-142): shift-1 = 64 + bs, 58 <= bs <= 62
     const u32 bs = S.shift - 1 - 64;
-    u64 lo = (sum[0].w1 >> bs) | (sum[0].w2 << (64 - bs));
-    u64 hi = (sum[0].w2 >> bs) | (sum[0].w3 << (64 - bs));
+    u64 lo = (sg.w1 >> bs) | (sg.w2 << (64 - bs));
+    u64 hi = (sg.w2 >> bs) | (sg.w3 << (64 - bs));
     u128 x = ((u128)hi << 64) | lo;
-    u128 v = (x >> 1) + (x & 1);
-    // w = round((sum_i +/- r_i * theta_omega_i -/+ v * theta_gamma) / 2^127)   (:294-314)
-    bool w_sign = false;
-    u128 w = 0;
-    if (!S.is_one) {
-      U256 so = u256_sub(sum[1], sum[2]);
-      U256 vt = u256_mul_128(v, S.tg_lo, S.tg_hi);
-      so = S.tg_sign ? u256_add(so, vt) : u256_sub(so, vt);
-      w_sign = (so.w3 != 0) || (so.w2 >> 63);
-      if (w_sign) {
-        u64 n1 = ~so.w1, n2 = ~so.w2, n3 = ~so.w3;
-        u128 y = ((u128)((n2 >> 62) | (n3 << 2)) << 64) | ((n1 >> 62) | (n2 << 2));
-        w = (y + 1) >> 1;
-      } else {
-        u128 y = ((u128)((so.w2 >> 62) | (so.w3 << 2)) << 64) | ((so.w1 >> 62) | (so.w2 << 2));
-        w = (y >> 1) + (y & 1);
-      }
-    }
-    sm.vw[0 * TC + cc] = (u64)v;
-    sm.vw[1 * TC + cc] = (u64)(v >> 64);
-    sm.vw[2 * TC + cc] = (u64)w;
-    sm.vw[3 * TC + cc] = (u64)(w >> 64);
-    sm.wsign[cc] = w_sign;
+    v = (x >> 1) + (x & 1);
   }
-  __syncthreads();
+  // w = round((sum_i +/- r_i * theta_omega_i -/+ v * theta_gamma) / 2^127)   (:276-314)
+  bool w_sign = false;
+  u128 w = 0;
+  if (!S.is_one) {
+    u32 pos[7] = {0, 0, 0, 0, 0, 0, 0}, neg[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (u32 i = 0; i < nf; i++) {
+      const u64 r = s_r[i * TC + cc];
+      if (s_tos[i]) mac_theta(neg, r, s_tol[i], s_toh[i]);   // table-driven, warp-uniform branch
+      else mac_theta(pos, r, s_tol[i], s_toh[i]);
+    }
+    U256 so = u256_sub(u256_from_acc(pos), u256_from_acc(neg));
+    U256 vt = u256_mul_128(v, S.tg_lo, S.tg_hi);
+    so = S.tg_sign ? u256_add(so, vt) : u256_sub(so, vt);
+    w_sign = (so.w3 != 0) || (so.w2 >> 63);
+    if (w_sign) {
+      u64 n1 = ~so.w1, n2 = ~so.w2, n3 = ~so.w3;
+      u128 y = ((u128)((n2 >> 62) | (n3 << 2)) << 64) | ((n1 >> 62) | (n2 << 2));
+      w = (y + 1) >> 1;
+    } else {
+      u128 y = ((u128)((so.w2 >> 62) | (so.w3 << 2)) << 64) | ((so.w1 >> 62) | (so.w2 << 2));
+      w = (y >> 1) + (y & 1);
+    }
+  }
 
-  // ---- outputs (:316-351): y_j = (-(v mod q_j) * gamma_j +/- w + sum_i r_i * omega_ji) mod q_j
-  const u64 v_lo = sm.vw[0 * TC + cc], v_hi = sm.vw[1 * TC + cc];
-  const u64 w_lo = sm.vw[2 * TC + cc], w_hi = sm.vw[3 * TC + cc];
-  const bool w_sign = sm.wsign[cc] != 0;
-  for (u32 j0 = g * 4; j0 < n_out; j0 += 16) {
+  // outputs (:316-351): y_j = (-(v mod q_j) * gamma_j +/- w + sum_i r_i * omega_ji) mod q_j, four limbs at a time
+  for (u32 j0 = 0; j0 < n_out; j0 += 4) {
     Acc192 acc[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) acc[k].clear();
-    const ulonglong2* om = reinterpret_cast<const ulonglong2*>(sm.omega + j0);
+    const ulonglong2* om = reinterpret_cast<const ulonglong2*>(s_omega + j0);
 #pragma unroll 2
     for (u32 i = 0; i < nf; i++) {
-      const u64 r = sm.r[i * TC + cc];
+      const u64 r = s_r[i * TC + cc];
       const ulonglong2 o0 = om[(size_t)i * (n_out4 / 2)], o1 = om[(size_t)i * (n_out4 / 2) + 1];
       acc[0].mac(r, o0.x);
       acc[1].mac(r, o0.y);
@@ -281,10 +236,10 @@ __global__ void __launch_bounds__(256) scale_kernel(ScaleArgs A) {
       const u32 jj = j0 + k;
       if (jj >= n_out) break;
       const LimbDev& M = A.limbs[S.to_ids[A.start + jj]];
-      u64 vr = reduce128_limb(v_lo, v_hi, M);
-      acc[k].mac(vr ? M.p - vr : 0, sm.gamma[jj]);
+      u64 vr = reduce128_limb((u64)v, (u64)(v >> 64), M);
+      acc[k].mac(vr ? M.p - vr : 0, s_gamma[jj]);
       if (!S.is_one) {
-        u64 wr = reduce128_limb(w_lo, w_hi, M);
+        u64 wr = reduce128_limb((u64)w, (u64)(w >> 64), M);
         acc[k].add64(w_sign ? (wr ? M.p - wr : 0) : wr);
       }
       u64 y = acc[k].reduce(M);
@@ -486,14 +441,13 @@ void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* 
     return;
   }
   const size_t n_out4 = (n_out + 3) & ~(size_t)3, nf = S.n_from;
-  const size_t smem = (nf * kScaleTC + nf * n_out4 + n_out4 + 5 * nf + 4 * kScaleTC) * sizeof(u64) +
-                      (3 * 4 * 7 * kScaleTC + kScaleTC) * sizeof(u32);
+  const size_t smem = (nf * kScaleTC + nf * n_out4 + n_out4 + 5 * nf) * sizeof(u64);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  scale_kernel<<<polys * (N / kScaleTC), 256, smem, st>>>(A);
+  scale_kernel<<<polys * (N / kScaleTC), kScaleTC, smem, st>>>(A);
   g_launches++;
 }
 

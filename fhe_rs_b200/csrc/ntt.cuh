@@ -183,7 +183,7 @@ __device__ __forceinline__ void ntt_tile_transform_mode(u64* sm, const LimbDev& 
 template <int LOGP, int LOGB, bool COLS, bool INV>
 __device__ __forceinline__ void ntt_tile_transform(u64* sm, const LimbDev& L, int s_base, u32 logn,
                                                    u32 row0, bool first_pass) {
-  if (L.sol_c) ntt_tile_transform_mode<LOGP, LOGB, COLS, INV, true>(sm, L, s_base, logn, row0, first_pass);
+  if (L.sol_ntt) ntt_tile_transform_mode<LOGP, LOGB, COLS, INV, true>(sm, L, s_base, logn, row0, first_pass);
   else ntt_tile_transform_mode<LOGP, LOGB, COLS, INV, false>(sm, L, s_base, logn, row0, first_pass);
 }
 

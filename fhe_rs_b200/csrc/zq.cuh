@@ -24,8 +24,8 @@ struct LimbDev {
   u64 zn;      // zetas_inv[N-2] * N^-1 mod p  (last inverse stage fused with the N^-1 scaling)
   u64 zn_s;    // shoup(zn)
   u64 c128;    // 2^128 mod p (folds the third accumulator word of lazy sums)
-  u64 sol_c;   // 0: generic prime, constant multiplications use Shoup pairs (w, floor(w*2^64/p));
-               // c: p = 2^62 - c with c < 2^28 ("Solinas" limb): pairs are (w, w*2^32 mod p), see mul_const_lazy
+  u64 sol_c;   // c if p = 2^62 - c with c < 2^28 ("Solinas" limb: lazy sums / products fold with 2^62 == c), else 0
+  u64 sol_ntt; // 1: twiddle pairs are (w, w*2^32 mod p) and the butterflies use mul_solinas_lazy; 0: Shoup pairs
   // twiddle tables as (value, companion) pairs so one 128-bit load fetches both words:
   const ulonglong2* om;  // omegas[N]    = psi^{bitrev(i)}       (ntt/native.rs:50-56) + Shoup quotient | w*2^32 mod p
   const ulonglong2* zi;  // zetas_inv[N] = psi^{-(bitrev(i)+1)}  + companion

@@ -274,3 +274,19 @@ def test_golden_fixture(oracle, F):
     assert (m.enable_mod_switching().multiply(A, B).to_host() == g["mul_relin_ms"]).all()
     assert (gk.relinearize(A).to_host() == g["galois3"]).all()
     assert (F.Ciphertext.from_host(gpar, g["a"]).into_power_basis().to_host() == g["a_pb"]).all()
+
+
+@pytest.mark.parametrize("env", [{"FHE_B200_SOLINAS_NTT": "1"}, {"FHE_B200_NO_SOLINAS": "1"}, {"FHE_B200_GENERIC_NTT": "1"},
+                                 {"FHE_B200_CHUNK": "1"}])
+def test_alternate_code_paths(F, env):
+    """the optional arithmetic / kernel variants (Solinas twiddle pairs, Barrett-only folds, generic tile NTT,
+    one-ciphertext chunks) must be bit-identical too: rerun the set-A multiply + the 2^13 NTT test under each switch"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                          "test_mul_relin_against_oracle and 4096 or test_ntt_forward_backward and 13-2 or "
+                          "test_ntt_forward_backward and 15-2 or test_golden_fixture"],
+                         cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
