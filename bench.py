@@ -37,6 +37,16 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ntt_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the two NTT tile kernels for one batched NTT of the roofline
+    shape, from the committed ncu --set full capture (profiles/ntt_traffic.json), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ntt_traffic.json")) as f:
+            return float(json.load(f)["bytes_per_batched_ntt"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason sampling during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -171,7 +181,7 @@ def cpu_baseline_sample():
     m = O.Multiplicator.default(O.RelinearizationKey.from_ksk(ksk))
     a, b = O.Ciphertext.from_array(par, rnd(2), 0), O.Ciphertext.from_array(par, rnd(2), 0)
     m.multiply(a, b)  # warm tables / page-in
-    n, t0 = 3, time.perf_counter()
+    n, t0 = 20, time.perf_counter()
     for _ in range(n):
         m.multiply(a, b)
     dt = time.perf_counter() - t0
@@ -255,25 +265,38 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the public host API with HOST buffers (pinned), copies inside the timed region
+    # ---- end to end through the public host API (C ABI) with HOST buffers: every step uploads the step's
+    # operands from pinned host memory, multiplies, and downloads the products; chunks of 32 pairs alternate
+    # between two streams so that PCIe copies overlap the kernels of the other chunk
     Be = min(args.e2e_batch, B)
-    words = Be * 2 * N_MODULI * DEGREE
-    ha = torch.empty(words, dtype=torch.int64).pin_memory()
-    hb = torch.empty(words, dtype=torch.int64).pin_memory()
-    ho = torch.empty(words, dtype=torch.int64).pin_memory()
-    ga = torch.as_tensor(DevArray(A.device_ptr(), words), device="cuda")
-    ha.copy_(ga); hb.copy_(torch.as_tensor(DevArray(Bt.device_ptr(), words), device="cuda"))
+    ch = min(32, Be)
+    Be -= Be % ch
+    wpc = 2 * N_MODULI * DEGREE                    # words per ciphertext
+    ha = torch.empty(Be * wpc, dtype=torch.int64).pin_memory()
+    hb = torch.empty(Be * wpc, dtype=torch.int64).pin_memory()
+    ho = torch.empty(Be * wpc, dtype=torch.int64).pin_memory()
+    ha.copy_(torch.as_tensor(DevArray(A.device_ptr(), Be * wpc), device="cuda"))
+    hb.copy_(torch.as_tensor(DevArray(Bt.device_ptr(), Be * wpc), device="cuda"))
     torch.cuda.synchronize()
-    Ae, Bte, oute = F.Ciphertext(par, Be, 2), F.Ciphertext(par, Be, 2), F.Ciphertext(par, Be, 2)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    slots = [(F.Ciphertext(par, ch, 2), F.Ciphertext(par, ch, 2), F.Ciphertext(par, ch, 2)) for _ in streams]
 
     def e2e_step():
-        check(L.fhe_b200_batch_upload(Ae._h, 0, Be, ha.data_ptr(), None))
-        check(L.fhe_b200_batch_upload(Bte._h, 0, Be, hb.data_ptr(), None))
-        check(L.fhe_b200_mul_relin(Ae._h, Bte._h, rk.ksk._h, 0, oute._h, None))
-        check(L.fhe_b200_batch_download(oute._h, 0, Be, ho.data_ptr(), None))   # synchronises
+        for k in range(Be // ch):
+            st = streams[k % 2].cuda_stream
+            sa, sb, so = slots[k % 2]
+            off = k * ch * wpc * 8
+            check(L.fhe_b200_batch_upload(sa._h, 0, ch, ha.data_ptr() + off, st))
+            check(L.fhe_b200_batch_upload(sb._h, 0, ch, hb.data_ptr() + off, st))
+            check(L.fhe_b200_mul_relin(sa._h, sb._h, rk.ksk._h, 0, so._h, st))
+            check(L.fhe_b200_batch_download_async(so._h, 0, ch, ho.data_ptr() + off, st))
+        for s_ in streams:
+            check(L.fhe_b200_sync(s_.cuda_stream))
 
     e2e_step()
     barrier()
+    assert bool((ho[: wpc] == torch.as_tensor(DevArray(out.device_ptr(), wpc), device="cuda").cpu()).all()), \
+        "e2e result differs from the device-resident run"
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
@@ -283,6 +306,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * Be * e2e_steps / float(e2e_s.item())
+    words = Be * wpc
 
     # ---- roofline of the dominant kernel family (NTT), BASELINE config 2: [256][8][2^14] forward + inverse
     roof = None
@@ -308,7 +332,7 @@ def main():
         peak, how = peaks()
         roof = {"bound": "hbm", "kernel": "ntt_cols_kernel+ntt_rows_kernel (one batched %d-row NTT, N=2^14)" % rows,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
-                "traffic": None, "ms_per_launch": ntt_ms,
+                "traffic": ntt_traffic(), "ms_per_launch": ntt_ms,
                 "note": "algorithmic bytes = 16*N per limb-NTT (SURVEY 8d); the transform is integer-issue bound "
                         "(about 28 integer instr per 62-bit Shoup butterfly), see DESIGN.md"}
 

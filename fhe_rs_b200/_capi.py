@@ -40,6 +40,7 @@ SYMBOLS = {
     "fhe_b200_batch_info": (_i, [_vp, _pu32, _pu32, _pu32, _pu32, C.POINTER(_i)]),
     "fhe_b200_batch_upload": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "fhe_b200_batch_download": (_i, [_vp, _u32, _u32, _vp, _vp]),
+    "fhe_b200_batch_download_async": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "fhe_b200_batch_copy": (_i, [_vp, _vp, _vp]),
     "fhe_b200_batch_device_ptr": (_i, [_vp, _pp, C.POINTER(C.c_size_t)]),
     "fhe_b200_ksk_upload": (_i, [_vp, _u32, _u32, _vp, _vp, _u32, _pp]),

@@ -246,6 +246,45 @@ void key_switch_core(const fhe_b200_params* par, const fhe_b200_ksk* k, const u6
                par->logn, st);
 }
 
+// key switch + the reference's post-processing (relinearization_key.rs:88-95, galois_key.rs:69-76):
+// when the key lives at a lower level number than the ciphertext (more moduli), the (c0, c1) pair is
+// taken to power basis, switched down to the ciphertext context and transformed back before it is added.
+// c2: [cts][L][N] power basis at the ciphertext level; out: [cts][2][L][N]; base (nullable) is added:
+// base_mode 0: none, 1: out += result (in place), 2: out = result + (base part 0 only; base is [cts][2][L][N])
+void key_switch_apply(const fhe_b200_params* par, const fhe_b200_ksk* k, const u64* c2, u32 cts, u64* out,
+                      int base_mode, u64* base, Workspace& ws, cudaStream_t st) {
+  const LevelData& cl = par->level(k->ct_level);
+  const u32 L = cl.L, Lk = k->Lk, logn = par->logn;
+  const size_t row = (size_t)1 << logn;
+  if (Lk == L) {
+    const u64* b0 = base_mode == 1 ? out : base_mode == 2 ? base : nullptr;
+    const u64* b1 = base_mode == 1 ? out + L * row : nullptr;
+    key_switch_core(par, k, c2, cts, b0, b1, out, out + L * row, 2 * L, ws, st);
+    return;
+  }
+  u64* cur = ws.words((size_t)cts * 2 * Lk * row);
+  key_switch_core(par, k, c2, cts, nullptr, nullptr, cur, cur + Lk * row, 2 * Lk, ws, st);
+  const LevelData& kl = par->level(k->ksk_level);
+  launch_ntt(cur, cur, cts * 2 * Lk, kl.ctx_ids, par->d_limbs, logn, true, 1, false, st);
+  for (u32 lv = k->ksk_level; lv < k->ct_level; lv++) {  // Poly::switch_down_to, rq/mod.rs:498-507
+    const LevelData& from = par->level(lv);
+    u64* nxt = ws.words((size_t)cts * 2 * (from.L - 1) * row);
+    launch_switch_down(from.sd, cur, nxt, cts * 2, from.L, from.ctx_ids, par->d_limbs, logn, st);
+    cur = nxt;
+  }
+  launch_ntt(cur, cur, cts * 2 * L, cl.ctx_ids, par->d_limbs, logn, false, 1, false, st);
+  if (base_mode == 1) {
+    launch_ew(EW_ADD, out, cur, (size_t)cts * 2 * L, cl.ctx_ids, par->d_limbs, logn, st);
+  } else {
+    FHE_CUDA(cudaMemcpyAsync(out, cur, (size_t)cts * 2 * L * row * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    if (base_mode == 2) {
+      // only part 0 of `base` takes part: clear its part 1 (a scratch buffer of the caller) and add everything
+      FHE_CUDA(cudaMemset2DAsync(base + L * row, 2 * L * row * sizeof(u64), 0, L * row * sizeof(u64), cts, st));
+      launch_ew(EW_ADD, out, base, (size_t)cts * 2 * L, cl.ctx_ids, par->d_limbs, logn, st);
+    }
+  }
+}
+
 // extend -> tensor -> scale down of bfv/ops/mul.rs:192-206 for `cts` ciphertext pairs.
 // a, b: [cts][2][L][N] NTT.  split == 0: out0 = [cts][3][L][N] power basis (all three parts);
 // split == 1: out0 = [cts][2][L][N] (c0, c1), out1 = [cts][L][N] (c2), all power basis.
@@ -513,6 +552,15 @@ int fhe_b200_batch_download(const fhe_b200_batch* b, uint32_t first, uint32_t n,
   FHE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   API_END
 }
+int fhe_b200_batch_download_async(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint64_t* host, void* stream) {
+  API_BEGIN
+  REQUIRE(b && host, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE((uint64_t)first + n <= b->count, FHE_B200_INVALID_ARGUMENT, "range exceeds batch");
+  DeviceGuard g(b->par);
+  size_t w = b->words_per_ct();
+  FHE_CUDA(cudaMemcpyAsync(host, b->d + w * first, w * n * sizeof(u64), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  API_END
+}
 int fhe_b200_batch_copy(fhe_b200_batch* dst, const fhe_b200_batch* src, void* stream) {
   API_BEGIN
   REQUIRE(dst && src, FHE_B200_INVALID_ARGUMENT, "null argument");
@@ -630,8 +678,6 @@ int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batc
 static void check_ksk(const fhe_b200_ksk* k, const fhe_b200_params* par, u32 level) {
   REQUIRE(k->par == par, FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch: key belongs to other parameters");
   REQUIRE(k->ct_level == level, FHE_B200_INVALID_LEVEL, "InvalidLevel: key is for another ciphertext level");
-  REQUIRE(k->ksk_level == k->ct_level, FHE_B200_UNSUPPORTED,
-          "key level != ciphertext level (switch-down after key switch) is not accelerated yet");
 }
 
 int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_b200_batch* out2, void* stream) {
@@ -658,7 +704,7 @@ int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_
     FHE_CUDA(cudaMemcpy2DAsync(c2, L * row * 8, src + 2 * L * row, 3 * L * row * 8, L * row * 8, n, cudaMemcpyDeviceToDevice, st));
     // relinearization_key.rs:85: c2 -> power basis
     launch_ntt(c2, c2, n * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
-    key_switch_core(par, rk, c2, n, dst, dst + L * row, dst, dst + L * row, 2 * (u32)L, ws, st);
+    key_switch_apply(par, rk, c2, n, dst, 1, nullptr, ws, st);
   }
   FHE_CUDA(cudaGetLastError());
   out2->repr = FHE_B200_NTT;
@@ -698,7 +744,7 @@ int fhe_b200_mul_relin(const fhe_b200_batch* a, const fhe_b200_batch* b, const f
     // c0, c1 back to NTT.  c2 stays in power basis: mul.rs:206 + :212 forward- then inverse-transform it,
     // and backward(forward(x)) == x for reduced x (ntt/mod.rs:73-74), so skipping both is bit-exact.
     launch_ntt(o, o, n * 2 * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
-    key_switch_core(par, rk, c2, n, o, o + L * row, o, o + L * row, 2 * (u32)L, ws, st);
+    key_switch_apply(par, rk, c2, n, o, 1, nullptr, ws, st);
     if (mod_switch) {  // Ciphertext::switch_down, ciphertext.rs:148-161
       launch_ntt(o, o, n * 2 * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
       u64* dst = out2->d + (size_t)c0 * 2 * (L - 1) * row;
@@ -759,7 +805,7 @@ int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_
     FHE_CUDA(cudaMemcpy2DAsync(c2, L * row * 8, s + L * row, 2 * L * row * 8, L * row * 8, n, cudaMemcpyDeviceToDevice, st));
     launch_ntt(c2, c2, n * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
     // galois_key.rs:67 + :78: out0 = key_switch0 + substitute(ct[0]); out1 = key_switch1
-    key_switch_core(par, gk, c2, n, s, nullptr, dst, dst + L * row, 2 * (u32)L, ws, st);
+    key_switch_apply(par, gk, c2, n, dst, 2, s, ws, st);
   }
   FHE_CUDA(cudaGetLastError());
   out->repr = FHE_B200_NTT;

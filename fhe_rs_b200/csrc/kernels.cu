@@ -236,10 +236,10 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
       const u32 jj = j0 + k;
       if (jj >= n_out) break;
       const LimbDev& M = A.limbs[S.to_ids[A.start + jj]];
-      u64 vr = reduce128_limb((u64)v, (u64)(v >> 64), M);
+      u64 vr = reduce94_limb((u64)v, (u64)(v >> 64), M);   // v < n_from * 2^63
       acc[k].mac(vr ? M.p - vr : 0, s_gamma[jj]);
       if (!S.is_one) {
-        u64 wr = reduce128_limb((u64)w, (u64)(w >> 64), M);
+        u64 wr = reduce94_limb((u64)w, (u64)(w >> 64), M); // w < 2^70
         acc[k].add64(w_sign ? (wr ? M.p - wr : 0) : wr);
       }
       u64 y = acc[k].reduce(M);

@@ -236,27 +236,29 @@ __device__ __forceinline__ void mul128_62(u64 a, u64 b, u64& lo, u64& hi) {
       : "l"(a), "l"(b));
 }
 
-// Reduction of a lazy sum V = hi*2^128 + mid*2^64 + lo (hi < 2^32) modulo p = 2^62 - c, c < 2^28, to [0,2p):
-// three folds of 2^62 == c (mod p).
-__device__ __forceinline__ u64 fold192_solinas(u64 lo, u64 mid, u64 hi, u32 c) {
-  typedef unsigned __int128 u128;
-  // fold 1: V1 = V >> 62 (up to 98 bits: v1a low 64, v1b high), V0 = V & (2^62-1)
+// One fold of 2^62 == c (mod p = 2^62 - c, c < 2^28) on a 128-bit value (hi:lo) with an extra
+// addend `top` for the word above (bits >= 126 of the quotient):  returns (hi':lo') == value (mod p),
+// (hi':lo') < 2^92 + top*c*2^64.  64-bit operations only (IMAD.WIDE + shifts).
+__device__ __forceinline__ void fold_step_solinas(u64& lo, u64& hi, u64 top, u32 c) {
   const u64 mask = (1ull << 62) - 1;
-  u64 v0 = lo & mask;
-  u64 v1a = (lo >> 62) | (mid << 2);
-  u64 v1b = (mid >> 62) | (hi << 2);                 // < 2^34
-  // U = V1*c + V0  (< 2^98*2^28 ... bounded by the caller: V < 2^160 is never reached; here V < 2^131 => V1 < 2^69)
-  u128 U = (u128)v1a * c + v0;
-  U += ((u128)(v1b * (u64)c)) << 64;                 // v1b*c < 2^62
-  // fold 2: U < 2^98  =>  U1 = U >> 62 < 2^36
-  u64 ulo = (u64)U, uhi = (u64)(U >> 64);
-  u64 u0 = ulo & mask;
-  u64 u1 = (ulo >> 62) | (uhi << 2);                 // < 2^36
-  u128 R = (u128)u1 * c + u0;                        // < 2^64 + 2^62
-  // fold 3
-  u64 rlo = (u64)R, rhi = (u64)(R >> 64);
-  u64 r1 = (rlo >> 62) | (rhi << 2);                 // < 2^3
-  return r1 * c + (rlo & mask);                      // < 2^31 + 2^62 < 2p
+  const u64 x = (lo >> 62) | (hi << 2);                 // quotient bits 62..125
+  const u64 t0 = (u64)c * (u32)x + (lo & mask);         // < 2^60 + 2^62
+  const u64 t1 = (u64)c * (u32)(x >> 32) + (t0 >> 32);  // < 2^60 + 2^31
+  lo = (t1 << 32) | (u32)t0;
+  hi = (t1 >> 32) + top * c;
+}
+// value (hi:lo) < 2^94 (hi < 2^30) -> [0,2p)
+__device__ __forceinline__ u64 fold94_solinas(u64 lo, u64 hi, u32 c) {
+  const u32 x = (u32)((lo >> 62) | (hi << 2));
+  return (u64)c * x + (lo & ((1ull << 62) - 1));         // < 2^60 + 2^62 < 2p
+}
+// Reduction of a lazy sum V = hi*2^128 + mid*2^64 + lo, hi < 2^16, modulo p = 2^62 - c to [0,2p):
+// 192 -> <2^111 -> <2^78 -> <2^62 + 2^44 bits.
+__device__ __forceinline__ u64 fold192_solinas(u64 lo, u64 mid, u64 hi, u32 c) {
+  u64 top = (mid >> 62) | (hi << 2);                     // quotient bits 126.. (< 2^18)
+  fold_step_solinas(lo, mid, top, c);                    // < 2^111
+  fold_step_solinas(lo, mid, 0, c);                      // < 2^78
+  return fold94_solinas(lo, mid, c);
 }
 
 // 192-bit lazy accumulator for sums of products of operands < 2^62 (used by the RNS scaler and the
@@ -294,6 +296,11 @@ struct Acc192 {
 // canonical residue of a 128-bit value
 __device__ __forceinline__ u64 reduce128_limb(u64 lo, u64 hi, const LimbDev& m) {
   if (m.sol_c) return csub(fold192_solinas(lo, hi, 0, (u32)m.sol_c), m.p);
+  return barrett128(lo, hi, m.p, m.bhi, m.blo);
+}
+// canonical residue of a value < 2^94 (the fixed-point quotients v, w of the scaler are < 2^70)
+__device__ __forceinline__ u64 reduce94_limb(u64 lo, u64 hi, const LimbDev& m) {
+  if (m.sol_c) return csub(fold94_solinas(lo, hi, (u32)m.sol_c), m.p);
   return barrett128(lo, hi, m.p, m.bhi, m.blo);
 }
 

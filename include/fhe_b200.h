@@ -104,6 +104,9 @@ int fhe_b200_batch_info(const fhe_b200_batch* b, uint32_t* count, uint32_t* part
 /* host <-> device copy of ciphertexts [first, first+n); host may be pageable or pinned. */
 int fhe_b200_batch_upload(fhe_b200_batch* b, uint32_t first, uint32_t n, const uint64_t* host, void* stream);
 int fhe_b200_batch_download(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint64_t* host, void* stream);
+/* same as download, but only enqueues the copy on `stream` (host must be pinned for it to be asynchronous);
+ * the caller waits with fhe_b200_sync(stream) before reading `host` */
+int fhe_b200_batch_download_async(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint64_t* host, void* stream);
 /* Ciphertext::clone: dst <- src (same parameters, shape, level; representation is copied) */
 int fhe_b200_batch_copy(fhe_b200_batch* dst, const fhe_b200_batch* src, void* stream);
 /* raw device pointer of the batch storage (for zero-copy producers such as bench.py). */

@@ -13,6 +13,16 @@ from bench import fill_uniform, DEGREE, N_MODULI, PLAINTEXT
 
 what = sys.argv[1] if len(sys.argv) > 1 else "mulrelin"
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+if what == "ntt14":  # BASELINE config 2: [256][8][2^14] forward + inverse (the bench.py roofline shape)
+    par = F.BfvParameters(1 << 14, PLAINTEXT, moduli_sizes=[62] * 8, device=0)
+    X = F.Ciphertext(par, 256, 1, repr=F.POWER_BASIS)
+    fill_uniform(torch, X, par.moduli(), 3)
+    for _ in range(3):
+        X.into_ntt()
+        X.into_power_basis()
+    torch.cuda.synchronize()
+    print("probe done ntt14")
+    sys.exit(0)
 par = F.BfvParameters(DEGREE, PLAINTEXT, moduli_sizes=[62] * N_MODULI, device=0)
 moduli = par.moduli()
 A = F.Ciphertext(par, count, 2)

@@ -290,3 +290,78 @@ def test_alternate_code_paths(F, env):
                           "test_ntt_forward_backward and 15-2 or test_golden_fixture"],
                          cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("degree,nmod,ct_level,key_level", [(16, 4, 1, 0), (64, 4, 2, 0), (4096, 3, 1, 0), (32, 3, 1, 1)])
+def test_leveled_keys(oracle, F, degree, nmod, ct_level, key_level):
+    """keys generated at a lower level number than the ciphertext (relinearization_key.rs:226-290,
+    galois_key.rs:69-76, mul.rs:215-222): key switch at the key level, switch_down_to the ciphertext level."""
+    t = 1153 if degree < 4096 else 1032193
+    opar, gpar, rng = make_pair(oracle, F, degree, nmod, t, 90 + nmod + ct_level)
+    sk, ork, grk, ogk, ggk = _keys(oracle, F, opar, gpar, rng, (3,), ct_level, key_level)
+    count = 2
+    ma, mb = rng.integers(0, t, size=(count, degree)), rng.integers(0, t, size=(count, degree))
+    octa = [sk.encrypt(m, ct_level, rng) for m in ma]
+    octb = [sk.encrypt(m, ct_level, rng) for m in mb]
+    A = F.Ciphertext.from_host(gpar, np.stack([c.to_array() for c in octa]), level=ct_level)
+    B = F.Ciphertext.from_host(gpar, np.stack([c.to_array() for c in octb]), level=ct_level)
+    C3 = A * B
+    got = grk.relinearizes(C3).to_host()
+    om = oracle.Multiplicator.default(ork)
+    gm = F.Multiplicator.default(grk)
+    gotm = gm.multiply(A, B).to_host()
+    gotg = ggk[3].relinearize(A).to_host()
+    for i in range(count):
+        exp = ork.relinearizes(octa[i].mul(octb[i]))
+        assert (got[i] == exp.to_array()).all()
+        assert (gotm[i] == om.multiply(octa[i], octb[i]).to_array()).all()
+        assert (gotg[i] == ogk[3].relinearize(octa[i]).to_array()).all()
+    # wrong level for this key
+    if ct_level > 0:
+        A0 = F.Ciphertext(gpar, count, 2, level=0)
+        with pytest.raises(F.FheError) as e:
+            ggk[3].relinearize(A0)
+        assert e.value.code == -6
+
+
+def test_full_size_set_c(oracle, F):
+    """BASELINE configs 3/4 shape: N = 2^15, 14 x 62-bit.  One product and one rotation bit-exact against the
+    oracle, plus size-independent properties on a batch: commutativity of the product (canonical outputs),
+    backward(forward(x)) == x, and (a + b) - b == a."""
+    degree, t, L = 1 << 15, 786433, 14
+    opar = oracle.BfvParameters(degree, t, moduli_sizes=[62] * L)
+    gpar = F.BfvParameters(degree, t, moduli_sizes=[62] * L)
+    assert gpar.moduli() == opar.moduli
+    rng = np.random.default_rng(2024)
+    ctx = opar.context_at_level(0)
+
+    def rnd(n, parts):
+        a = np.zeros((n, parts, L, degree), np.uint64)
+        for i, q in enumerate(ctx.moduli):
+            a[:, :, i, :] = rng.integers(0, q, size=(n, parts, degree), dtype=np.uint64)
+        return a
+    kc = rnd(2, L)          # random key material is enough for bit-exactness
+    gc = rnd(2, L)
+    ork = oracle.RelinearizationKey.from_ksk(oracle.KeySwitchingKey.from_arrays(opar, kc[0], kc[1]))
+    grk = F.RelinearizationKey.from_arrays(gpar, kc[0], kc[1])
+    count = 3
+    a, b = rnd(count, 2), rnd(count, 2)
+    A, B = F.Ciphertext.from_host(gpar, a), F.Ciphertext.from_host(gpar, b)
+    gm = F.Multiplicator.default(grk)
+    P = gm.multiply(A, B).to_host()
+    exp = oracle.Multiplicator.default(ork).multiply(oracle.Ciphertext.from_array(opar, a[0], 0),
+                                                     oracle.Ciphertext.from_array(opar, b[0], 0))
+    assert (P[0] == exp.to_array()).all()
+    assert (gm.multiply(B, A).to_host() == P).all()
+    # rotation (config 4)
+    ogk = oracle.GaloisKey.__new__(oracle.GaloisKey)
+    ogk.exponent, ogk.ksk = 3, oracle.KeySwitchingKey.from_arrays(opar, gc[0], gc[1])
+    ggk = F.GaloisKey.from_arrays(gpar, 3, gc[0], gc[1])
+    R = ggk.relinearize(A).to_host()
+    assert (R[0] == ogk.relinearize(oracle.Ciphertext.from_array(opar, a[0], 0)).to_array()).all()
+    # NTT round trip and add/sub on the batch
+    X = F.Ciphertext.from_host(gpar, a)
+    assert (X.into_power_basis().into_ntt().to_host() == a).all()
+    S = A + B
+    S -= B
+    assert (S.to_host() == a).all()
