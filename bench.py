@@ -333,8 +333,14 @@ def main():
         roof = {"bound": "hbm", "kernel": "ntt_cols_kernel+ntt_rows_kernel (one batched %d-row NTT, N=2^14)" % rows,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
                 "traffic": ntt_traffic(), "ms_per_launch": ntt_ms,
-                "note": "algorithmic bytes = 16*N per limb-NTT (SURVEY 8d); the transform is integer-issue bound "
-                        "(about 28 integer instr per 62-bit Shoup butterfly), see DESIGN.md"}
+                "note": "algorithmic bytes = 16*N per limb-NTT (SURVEY 8d). The transform is integer-issue bound, not "
+                        "HBM bound: see issue_roofline and DESIGN.md section 3",
+                # second roofline for the same launches: 62-bit Harvey/Shoup butterflies per second against the
+                # measured peak of this pool's B200 (bench_micro/bf_bench.cu: 3.21 butterflies/clk/SM at 1.9 GHz)
+                "issue_roofline": {"unit": "T butterflies/s",
+                                   "achieved": rows * (NTT_CFG["degree"] // 2) * 14 / (ntt_ms * 1e-3) / 1e12,
+                                   "peak": 0.902, "peak_source": "measured, profiles/microbench_r1.txt",
+                                   "frac": rows * (NTT_CFG["degree"] // 2) * 14 / (ntt_ms * 1e-3) / 1e12 / 0.902}}
 
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline_sample()
