@@ -107,7 +107,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
-    workers = max(1, min(cores, 32))
+    workers = max(1, min(cores, 256))   # every host core: one ciphertext pair per worker per step
     ctx = mp.get_context("fork")
     barrier = ctx.Barrier(workers + 1)
     q = ctx.Queue()

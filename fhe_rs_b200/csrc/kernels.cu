@@ -329,29 +329,48 @@ struct KsMacArgs {
   unsigned short ids[kMaxPos];
 };
 // out0 = base0 + sum_i t_i * k0_i ; out1 = base1 + sum_i t_i * k1_i   (key_switching_key.rs:256-268)
+// One thread owns coefficient (j, c) of CTB consecutive ciphertexts: each key word is fetched once per
+// CTB ciphertexts (the 103 MB key does not stay in L2 next to the streaming digit rows; ncu: the
+// one-ciphertext form moved 154 MB per ciphertext).
+template <int CTB>
 __global__ void ksmac_kernel(KsMacArgs A) {
   const u32 N = 1u << A.logn;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over cts*Lk*N
-  size_t total = ((size_t)A.cts * A.Lk) << A.logn;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over ceil(cts/CTB)*Lk*N
+  const u32 groups = (A.cts + CTB - 1) / CTB;
+  size_t total = ((size_t)groups * A.Lk) << A.logn;
   if (idx >= total) return;
   u32 c = idx & (N - 1);
   size_t row = idx >> A.logn;
-  u32 j = row % A.Lk, ct = row / A.Lk;
+  u32 j = row % A.Lk, ct0 = (u32)(row / A.Lk) * CTB;
   const LimbDev& M = A.limbs[A.ids[j]];
-  Acc192 a0, a1;
-  a0.clear();
-  a1.clear();
-  for (u32 i = 0; i < A.n_dig; i++) {
-    u64 t = A.inter[((((size_t)ct * A.n_dig + i) * A.Lk + j) << A.logn) + c];
-    size_t ko = (((size_t)i * A.Lk + j) << A.logn) + c;
-    a0.mac(t, __ldg(A.k0 + ko));
-    a1.mac(t, __ldg(A.k1 + ko));
+  Acc192 a0[CTB], a1[CTB];
+#pragma unroll
+  for (int q = 0; q < CTB; q++) {
+    a0[q].clear();
+    a1[q].clear();
   }
-  size_t o = (((size_t)ct * A.out_ct_rows + j) << A.logn) + c;
-  if (A.base0) a0.add64(A.base0[o]);
-  if (A.base1) a1.add64(A.base1[o]);
-  A.out0[o] = a0.reduce(M);
-  A.out1[o] = a1.reduce(M);
+  for (u32 i = 0; i < A.n_dig; i++) {
+    const size_t ko = (((size_t)i * A.Lk + j) << A.logn) + c;
+    const u64 k0 = __ldg(A.k0 + ko), k1 = __ldg(A.k1 + ko);
+#pragma unroll
+    for (int q = 0; q < CTB; q++) {
+      if (ct0 + q < A.cts) {
+        const u64 t = A.inter[((((size_t)(ct0 + q) * A.n_dig + i) * A.Lk + j) << A.logn) + c];
+        a0[q].mac(t, k0);
+        a1[q].mac(t, k1);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < CTB; q++) {
+    if (ct0 + q < A.cts) {
+      const size_t o = (((size_t)(ct0 + q) * A.out_ct_rows + j) << A.logn) + c;
+      if (A.base0) a0[q].add64(A.base0[o]);
+      if (A.base1) a1[q].add64(A.base1[o]);
+      A.out0[o] = a0[q].reduce(M);
+      A.out1[o] = a1[q].reduce(M);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ gather / switch_down
@@ -459,9 +478,10 @@ void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* bas
   A.cts = cts; A.n_dig = n_dig; A.Lk = Lk; A.out_ct_rows = out_ct_rows; A.logn = logn;
   A.limbs = limbs;
   copy_ids(A.ids, ids);
-  size_t total = ((size_t)cts * Lk) << logn;
-  if (!total) return;
-  ksmac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+  if (!cts) return;
+  constexpr int CTB = 4;
+  size_t total = ((size_t)((cts + CTB - 1) / CTB) * Lk) << logn;
+  ksmac_kernel<CTB><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(A);
   g_launches++;
 }
 

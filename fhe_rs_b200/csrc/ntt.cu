@@ -33,7 +33,7 @@ void run_cols(const NttArgs& a, cudaStream_t st) {
 
 template <int LOGP, bool COLS, bool INV>
 void run_fast(const NttArgs& a, cudaStream_t st) {
-  constexpr size_t smem = 2 * (4096 + 128) * sizeof(u64);
+  constexpr size_t smem = 2 * 4672 * sizeof(u64);
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaFuncSetAttribute(ntt_fast_kernel<LOGP, COLS, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -23,7 +23,19 @@ struct FastTile {
   static constexpr u32 P = 1u << LOGP, B = 1u << LOGB;
   static constexpr int NR = (LOGP + 2) / 3;
   static constexpr int REM = LOGP - 3 * (NR - 1);
-  static constexpr u32 TW = 4096 + 128;  // padded words per tile buffer
+  static constexpr u32 TW = 4672;  // padded words per tile buffer (>= 4096 + 512 + 8)
+  // Shared-memory padding.  cols layout: i + i/32.  rows layout with 64-point rows: i + 8*(i/64) + (i/8)%8, which makes
+  // both exchange patterns of the pass (8 lanes x 4 rows at stride 8, and 8-word runs) hit 16 distinct bank pairs
+  // (the i + i/32 padding left the stride-8 pattern 4-way conflicted: 8.7M conflicts per launch in profiles/r1_ntt_*).
+  static constexpr bool ROWS6 = !COLS && LOGP == 6;
+  static __device__ __forceinline__ u32 phys(u32 i) {
+    return ROWS6 ? i + ((i >> 6) << 3) + ((i >> 3) & 7) : i + (i >> 5);
+  }
+  // offset of element e (stride S words) of a radix group relative to phys(group base); the group's bit field is
+  // zero in the base index, so the padding terms add without carries
+  static __host__ __device__ constexpr u32 delta(u32 e, u32 S) {
+    return ROWS6 ? (S == 8 ? 9 * e : e) : e * S + ((e * S) >> 5);
+  }
 
   // geometry of round r for this thread: NS stages starting at local stage t = 3r
   template <int NS>
@@ -143,9 +155,9 @@ struct FastTile {
           x[q * R + e] = v;
         }
       } else {
-        const u64* ptr = sm_in + sm_phys(tile_index<NS>(g, q));
+        const u64* ptr = sm_in + phys(tile_index<NS>(g, q));
 #pragma unroll
-        for (int e = 0; e < R; e++) x[q * R + e] = ptr[pad_delta(e, S)];
+        for (int e = 0; e < R; e++) x[q * R + e] = ptr[delta(e, S)];
       }
     }
     compute<NS>(x, g, L, t, s_base, logn, row0, first_pass);
@@ -157,9 +169,9 @@ struct FastTile {
 #pragma unroll
         for (int e = 0; e < R; e++) ptr[e * gs] = x[q * R + e];
       } else {
-        u64* ptr = sm_out + sm_phys(tile_index<NS>(g, q));
+        u64* ptr = sm_out + phys(tile_index<NS>(g, q));
 #pragma unroll
-        for (int e = 0; e < R; e++) ptr[pad_delta(e, S)] = x[q * R + e];
+        for (int e = 0; e < R; e++) ptr[delta(e, S)] = x[q * R + e];
       }
     }
   }
@@ -172,27 +184,18 @@ struct FastTile {
   static __device__ __forceinline__ void stage_in(const u64* __restrict__ src, u64* buf, bool reduce_on_load,
                                                   const LimbDev& L) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const u32 i = (k * 512 + threadIdx.x) * 2;
-      ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + i);
-      if (reduce_on_load) {
-        v.x = barrett64(v.x, L.p, L.bhi, L.blo);
-        v.y = barrett64(v.y, L.p, L.bhi, L.blo);
-      }
-      const u32 ph = sm_phys(i);
-      buf[ph] = v.x;
-      buf[ph + 1] = v.y;
+    for (int k = 0; k < 8; k++) {
+      const u32 i = k * 512 + threadIdx.x;   // consecutive lanes -> consecutive words: 256 B per request, no conflicts
+      u64 v = src[i];
+      if (reduce_on_load) v = barrett64(v, L.p, L.bhi, L.blo);
+      buf[phys(i)] = v;
     }
   }
   static __device__ __forceinline__ void stage_out(u64* __restrict__ dst, const u64* buf) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const u32 i = (k * 512 + threadIdx.x) * 2;
-      const u32 ph = sm_phys(i);
-      ulonglong2 v;
-      v.x = buf[ph];
-      v.y = buf[ph + 1];
-      *reinterpret_cast<ulonglong2*>(dst + i) = v;
+    for (int k = 0; k < 8; k++) {
+      const u32 i = k * 512 + threadIdx.x;
+      dst[i] = buf[phys(i)];
     }
   }
 
