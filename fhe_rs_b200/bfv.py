@@ -233,6 +233,31 @@ class Ciphertext:
         check(_capi.lib().fhe_b200_batch_download(self._h, 0, out.shape[0], _ptr(out), self.stream))
         return out
 
+    # -- wire format (rq/convert.rs:17-131): Rq.coefficients blobs, one per polynomial
+    def packed_bytes_per_poly(self) -> int:
+        n = C.c_size_t()
+        check(_capi.lib().fhe_b200_poly_packed_bytes(self.par._h, self.level, C.byref(n)))
+        return n.value
+
+    def to_packed(self) -> np.ndarray:
+        """[count][parts][packed_bytes] uint8: what `Rq::from(&poly).coefficients` holds for every polynomial"""
+        c, p, _, _, _ = self._info()
+        out = np.empty((c, p, self.packed_bytes_per_poly()), np.uint8)
+        check(_capi.lib().fhe_b200_batch_pack(self._h, 0, c, _ptr(out), self.stream))
+        return out
+
+    @staticmethod
+    def from_packed(par: "BfvParameters", blobs: np.ndarray, level: int = 0, repr: int = NTT,
+                    stream: int = 0) -> "Ciphertext":
+        """inverse of to_packed: `Poly::<R>::try_convert_from(&Rq, ctx, ..)` for every polynomial"""
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
+        ct = Ciphertext(par, blobs.shape[0], blobs.shape[1], level, repr, stream)
+        if blobs.shape[2] != ct.packed_bytes_per_poly():
+            raise FheError(_capi.INVALID_ARGUMENT, "InvalidCoefficientCount: blob size does not match the context")
+        check(_capi.lib().fhe_b200_batch_unpack(ct._h, 0, blobs.shape[0], _ptr(blobs), stream))
+        check(_capi.lib().fhe_b200_sync(stream))
+        return ct
+
     def device_ptr(self) -> int:
         p, n = C.c_void_p(), C.c_size_t()
         check(_capi.lib().fhe_b200_batch_device_ptr(self._h, C.byref(p), C.byref(n)))

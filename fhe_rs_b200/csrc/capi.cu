@@ -906,6 +906,78 @@ int fhe_b200_scale(const fhe_b200_batch* in, int which, fhe_b200_batch* out, voi
   API_END
 }
 
+// ------------------------------------------------------------------------------ wire format
+static PackDev pack_desc(const fhe_b200_batch* b) {
+  const fhe_b200_params* par = b->par;
+  const LevelData& lv = par->level(b->level);
+  PackDev P;
+  std::memset(&P, 0, sizeof(P));
+  P.limbs = b->limbs;
+  u32 off = 0;
+  for (u32 i = 0; i < b->limbs; i++) {
+    const u64 q = b->mul_basis ? lv.mul_moduli[i] : par->moduli[i];
+    const u32 nb = 64 - (u32)clz64(q - 1);          // Modulus::serialize_vec, zq/mod.rs:784
+    P.nbits[i] = (unsigned char)nb;
+    P.offs[i] = off;
+    off += nb * (par->N / 8);                        // serialization_length, zq/mod.rs:773-777
+  }
+  P.poly_bytes = off;
+  return P;
+}
+int fhe_b200_poly_packed_bytes(const fhe_b200_params* p, uint32_t level, size_t* nbytes) {
+  API_BEGIN
+  REQUIRE(p && nbytes, FHE_B200_INVALID_ARGUMENT, "null argument");
+  const LevelData& lv = p->level(level);
+  size_t n = 0;
+  for (u32 i = 0; i < lv.L; i++) n += (size_t)(64 - clz64(p->moduli[i] - 1)) * (p->N / 8);
+  *nbytes = n;
+  API_END
+}
+int fhe_b200_batch_pack(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint8_t* host_out, void* stream) {
+  API_BEGIN
+  REQUIRE(b && host_out, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE((uint64_t)first + n <= b->count, FHE_B200_INVALID_ARGUMENT, "range exceeds batch");
+  const fhe_b200_params* par = b->par;
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const PackDev P = pack_desc(b);
+  const size_t rows = (size_t)n * b->parts * b->limbs, row = (size_t)1 << par->logn;
+  Workspace ws(st);
+  const u64* src = b->d + b->words_per_ct() * first;
+  if (b->repr == FHE_B200_NTT) {   // rq/convert.rs:20-24: serialization is always in power basis
+    u64* pb = ws.words(rows * row);
+    launch_ntt(src, pb, (u32)rows, ids_of(b), par->d_limbs, par->logn, true, 1, false, st);
+    src = pb;
+  }
+  const size_t nbytes = (size_t)n * b->parts * P.poly_bytes;
+  unsigned char* dbytes = (unsigned char*)ws.words((nbytes + 7) / 8);
+  launch_pack(P, src, dbytes, rows, par->logn, st);
+  FHE_CUDA(cudaGetLastError());
+  FHE_CUDA(cudaMemcpyAsync(host_out, dbytes, nbytes, cudaMemcpyDeviceToHost, st));
+  FHE_CUDA(cudaStreamSynchronize(st));
+  API_END
+}
+int fhe_b200_batch_unpack(fhe_b200_batch* b, uint32_t first, uint32_t n, const uint8_t* host_in, void* stream) {
+  API_BEGIN
+  REQUIRE(b && host_in, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE((uint64_t)first + n <= b->count, FHE_B200_INVALID_ARGUMENT, "range exceeds batch");
+  const fhe_b200_params* par = b->par;
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const PackDev P = pack_desc(b);
+  const size_t rows = (size_t)n * b->parts * b->limbs;
+  Workspace ws(st);
+  const size_t nbytes = (size_t)n * b->parts * P.poly_bytes;
+  unsigned char* dbytes = (unsigned char*)ws.words((nbytes + 7) / 8);
+  FHE_CUDA(cudaMemcpyAsync(dbytes, host_in, nbytes, cudaMemcpyHostToDevice, st));
+  u64* dst = b->d + b->words_per_ct() * first;
+  launch_unpack(P, dbytes, dst, rows, par->logn, st);
+  if (b->repr == FHE_B200_NTT)     // rq/convert.rs:128-129: p.into_ntt()
+    launch_ntt(dst, dst, (u32)rows, ids_of(b), par->d_limbs, par->logn, false, 1, false, st);
+  FHE_CUDA(cudaGetLastError());
+  API_END
+}
+
 int fhe_b200_sync(void* stream) {
   API_BEGIN
   FHE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));

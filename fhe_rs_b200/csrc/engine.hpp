@@ -82,4 +82,15 @@ struct SwitchDownDev {
 void launch_switch_down(const SwitchDownDev& S, const u64* in, u64* out, u32 polys, u32 L, const RowIds& ids,
                         const LimbDev* limbs, u32 logn, cudaStream_t st);
 
+// bit (un)packing of power-basis rows (fhe-util/src/lib.rs:71-146): row r of `rows` uses nbits[r % limbs] bits per
+// coefficient; packed row r starts at byte  (r / limbs) * poly_bytes + offs[r % limbs]
+struct PackDev {
+  u32 limbs;
+  unsigned char nbits[kMaxPos];
+  u32 offs[kMaxPos];
+  u32 poly_bytes;
+};
+void launch_pack(const PackDev& P, const u64* words, unsigned char* bytes, size_t n_rows, u32 logn, cudaStream_t st);
+void launch_unpack(const PackDev& P, const unsigned char* bytes, u64* words, size_t n_rows, u32 logn, cudaStream_t st);
+
 }  // namespace fhe_b200

@@ -329,48 +329,45 @@ struct KsMacArgs {
   unsigned short ids[kMaxPos];
 };
 // out0 = base0 + sum_i t_i * k0_i ; out1 = base1 + sum_i t_i * k1_i   (key_switching_key.rs:256-268)
-// One thread owns coefficient (j, c) of CTB consecutive ciphertexts: each key word is fetched once per
-// CTB ciphertexts (the 103 MB key does not stay in L2 next to the streaming digit rows; ncu: the
-// one-ciphertext form moved 154 MB per ciphertext).
-template <int CTB>
+// One thread per (limb j, ciphertext, coefficient), limb-major: consecutive CTAs work on the same key limb for
+// every ciphertext of the chunk, so the 2 x n_dig key rows of that limb (7 MB at set C) stay in L2 while the digit
+// rows stream through -- each key word leaves HBM once per chunk instead of once per ciphertext.
 __global__ void ksmac_kernel(KsMacArgs A) {
   const u32 N = 1u << A.logn;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over ceil(cts/CTB)*Lk*N
-  const u32 groups = (A.cts + CTB - 1) / CTB;
-  size_t total = ((size_t)groups * A.Lk) << A.logn;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over Lk*cts*N
+  size_t total = ((size_t)A.cts * A.Lk) << A.logn;
   if (idx >= total) return;
   u32 c = idx & (N - 1);
   size_t row = idx >> A.logn;
-  u32 j = row % A.Lk, ct0 = (u32)(row / A.Lk) * CTB;
+  u32 ct = row % A.cts, j = row / A.cts;
   const LimbDev& M = A.limbs[A.ids[j]];
-  Acc192 a0[CTB], a1[CTB];
-#pragma unroll
-  for (int q = 0; q < CTB; q++) {
-    a0[q].clear();
-    a1[q].clear();
+  Acc192 a0, a1;
+  a0.clear();
+  a1.clear();
+  const u64* t_ptr = A.inter + ((((size_t)ct * A.n_dig) * A.Lk + j) << A.logn) + c;
+  const u64* k0_ptr = A.k0 + ((size_t)j << A.logn) + c;
+  const u64* k1_ptr = A.k1 + ((size_t)j << A.logn) + c;
+  const size_t dstride = (size_t)A.Lk << A.logn;
+  u32 i = 0;
+  for (; i + 2 <= A.n_dig; i += 2) {   // two digits per trip: six independent loads in flight
+    const u64 t0 = t_ptr[(size_t)i * dstride], t1 = t_ptr[(size_t)(i + 1) * dstride];
+    const u64 x0 = __ldg(k0_ptr + (size_t)i * dstride), x1 = __ldg(k0_ptr + (size_t)(i + 1) * dstride);
+    const u64 y0 = __ldg(k1_ptr + (size_t)i * dstride), y1 = __ldg(k1_ptr + (size_t)(i + 1) * dstride);
+    a0.mac(t0, x0);
+    a1.mac(t0, y0);
+    a0.mac(t1, x1);
+    a1.mac(t1, y1);
   }
-  for (u32 i = 0; i < A.n_dig; i++) {
-    const size_t ko = (((size_t)i * A.Lk + j) << A.logn) + c;
-    const u64 k0 = __ldg(A.k0 + ko), k1 = __ldg(A.k1 + ko);
-#pragma unroll
-    for (int q = 0; q < CTB; q++) {
-      if (ct0 + q < A.cts) {
-        const u64 t = A.inter[((((size_t)(ct0 + q) * A.n_dig + i) * A.Lk + j) << A.logn) + c];
-        a0[q].mac(t, k0);
-        a1[q].mac(t, k1);
-      }
-    }
+  if (i < A.n_dig) {
+    const u64 t0 = t_ptr[(size_t)i * dstride];
+    a0.mac(t0, __ldg(k0_ptr + (size_t)i * dstride));
+    a1.mac(t0, __ldg(k1_ptr + (size_t)i * dstride));
   }
-#pragma unroll
-  for (int q = 0; q < CTB; q++) {
-    if (ct0 + q < A.cts) {
-      const size_t o = (((size_t)(ct0 + q) * A.out_ct_rows + j) << A.logn) + c;
-      if (A.base0) a0[q].add64(A.base0[o]);
-      if (A.base1) a1[q].add64(A.base1[o]);
-      A.out0[o] = a0[q].reduce(M);
-      A.out1[o] = a1[q].reduce(M);
-    }
-  }
+  const size_t o = (((size_t)ct * A.out_ct_rows + j) << A.logn) + c;
+  if (A.base0) a0.add64(A.base0[o]);
+  if (A.base1) a1.add64(A.base1[o]);
+  A.out0[o] = a0.reduce(M);
+  A.out1[o] = a1.reduce(M);
 }
 
 // ------------------------------------------------------------------ gather / switch_down
@@ -404,6 +401,56 @@ __global__ void switch_down_kernel(SwitchDownArgs A) {
     u64 tmp = barrett64(xl, M.p, M.bhi, M.blo) + A.S.half_mod[i];   // :469
     u64 v = src[(size_t)i << A.logn] + 3 * M.p - tmp;              // :473
     dst[(size_t)i << A.logn] = mul_shoup(v, A.S.inv[i], A.S.inv_s[i], M.p);  // :476 (always a Shoup pair)
+  }
+}
+
+// ------------------------------------------------------------------ wire-format bit packing
+// transcode_to_bytes / transcode_from_bytes (fhe-util/src/lib.rs:71-146): eight coefficients of nbits bits are
+// exactly nbits bytes, so one thread converts one 8-coefficient group.
+__global__ void pack_kernel(PackDev P, const u64* words, unsigned char* bytes, size_t n_groups, u32 logn) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const u32 gpr = (1u << logn) >> 3;            // groups per row
+  const size_t row = g / gpr;
+  const u32 k = (u32)(g % gpr), limb = (u32)(row % P.limbs);
+  const u32 nb = P.nbits[limb];
+  const u64* src = words + (row << logn) + ((size_t)k << 3);
+  unsigned char* dst = bytes + (row / P.limbs) * P.poly_bytes + P.offs[limb] + (size_t)k * nb;
+  const u64 mask = nb == 64 ? ~0ull : ((1ull << nb) - 1);
+  unsigned __int128 cur = 0;
+  u32 have = 0, o = 0;
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    cur |= (unsigned __int128)(src[e] & mask) << have;
+    have += nb;
+    while (have >= 8) {
+      dst[o++] = (unsigned char)cur;
+      cur >>= 8;
+      have -= 8;
+    }
+  }
+}
+__global__ void unpack_kernel(PackDev P, const unsigned char* bytes, u64* words, size_t n_groups, u32 logn) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const u32 gpr = (1u << logn) >> 3;
+  const size_t row = g / gpr;
+  const u32 k = (u32)(g % gpr), limb = (u32)(row % P.limbs);
+  const u32 nb = P.nbits[limb];
+  const unsigned char* src = bytes + (row / P.limbs) * P.poly_bytes + P.offs[limb] + (size_t)k * nb;
+  u64* dst = words + (row << logn) + ((size_t)k << 3);
+  const u64 mask = nb == 64 ? ~0ull : ((1ull << nb) - 1);
+  unsigned __int128 cur = 0;
+  u32 have = 0, o = 0;
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    while (have < nb) {
+      cur |= (unsigned __int128)src[o++] << have;
+      have += 8;
+    }
+    dst[e] = (u64)cur & mask;
+    cur >>= nb;
+    have -= nb;
   }
 }
 
@@ -478,10 +525,9 @@ void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* bas
   A.cts = cts; A.n_dig = n_dig; A.Lk = Lk; A.out_ct_rows = out_ct_rows; A.logn = logn;
   A.limbs = limbs;
   copy_ids(A.ids, ids);
-  if (!cts) return;
-  constexpr int CTB = 4;
-  size_t total = ((size_t)((cts + CTB - 1) / CTB) * Lk) << logn;
-  ksmac_kernel<CTB><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(A);
+  size_t total = ((size_t)cts * Lk) << logn;
+  if (!total) return;
+  ksmac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
   g_launches++;
 }
 
@@ -489,6 +535,19 @@ void launch_gather(const u64* in, u64* out, size_t n_rows, const int* perm, u32 
   size_t n = n_rows << logn;
   if (!n) return;
   gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, perm, logn);
+  g_launches++;
+}
+
+void launch_pack(const PackDev& P, const u64* words, unsigned char* bytes, size_t n_rows, u32 logn, cudaStream_t st) {
+  const size_t groups = n_rows << (logn - 3);
+  if (!groups) return;
+  pack_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(P, words, bytes, groups, logn);
+  g_launches++;
+}
+void launch_unpack(const PackDev& P, const unsigned char* bytes, u64* words, size_t n_rows, u32 logn, cudaStream_t st) {
+  const size_t groups = n_rows << (logn - 3);
+  if (!groups) return;
+  unpack_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(P, bytes, words, groups, logn);
   g_launches++;
 }
 

@@ -235,6 +235,14 @@ struct FastTile {
   }
 };
 
+// blockIdx -> (row, tile), row-major: consecutive CTAs sweep one 8N-byte row.  (A polynomial-minor order, which
+// lets co-resident CTAs share a twiddle block in L1, was measured 4-6% slower: it scatters the HBM accesses over
+// many rows at once -- profiles/r1_launches_* history in DESIGN.md.)
+__device__ __forceinline__ void decode_block(const NttArgs& A, u32 tiles, u32& row, u32& tile) {
+  row = blockIdx.x / tiles;
+  tile = blockIdx.x % tiles;
+}
+
 template <int LOGP, bool COLS, bool INV>
 __global__ void __launch_bounds__(512, 2) ntt_fast_kernel(NttArgs A) {
   extern __shared__ u64 sm[];
@@ -247,16 +255,14 @@ __global__ void __launch_bounds__(512, 2) ntt_fast_kernel(NttArgs A) {
   if (COLS) {
     const u32 logn2 = A.logn - LOGP;
     const u32 tiles = (1u << logn2) >> LOGB;
-    row = blockIdx.x / tiles;
-    tile = blockIdx.x % tiles;
+    decode_block(A, tiles, row, tile);
     src = A.in + ((size_t)(row / A.in_div) << A.logn) + (tile << LOGB);
     dst = A.out + ((size_t)row << A.logn) + (tile << LOGB);
     gstride_a = 1u << logn2;
     s_base = 0;
   } else {
     const u32 tiles = (1u << A.logn1) >> LOGB;
-    row = blockIdx.x / tiles;
-    tile = blockIdx.x % tiles;
+    decode_block(A, tiles, row, tile);
     src = A.in + ((size_t)(row / A.in_div) << A.logn) + ((size_t)tile << 12);
     dst = A.out + ((size_t)row << A.logn) + ((size_t)tile << 12);
     row0 = tile << LOGB;

@@ -159,6 +159,21 @@ int fhe_b200_scale(const fhe_b200_batch* in, int which, fhe_b200_batch* out, voi
 int fhe_b200_batch_alloc_mul_basis(const fhe_b200_params* p, uint32_t count, uint32_t parts, uint32_t level,
                                    int repr, fhe_b200_batch** out);
 
+/* ---- wire format of polynomials -------------------------------------------
+ * `Rq.coefficients` of the reference's protobuf message (fhe-math/src/proto/rq.proto:12-17) is, for every limb
+ * in order, the power-basis coefficients bit-packed LSB first with ceil(log2 q_i) bits each
+ * (Modulus::serialize_vec zq/mod.rs:783-786, fhe_util::transcode_to_bytes fhe-util/src/lib.rs:71-108).
+ * The protobuf framing itself (tags, varints, `representation`, `degree`) stays with the host's prost code. */
+/* Modulus::serialization_length summed over the limbs of `level` (rq/convert.rs:78-82): bytes per polynomial */
+int fhe_b200_poly_packed_bytes(const fhe_b200_params* p, uint32_t level, size_t* nbytes);
+/* From<&Poly<R>> for Rq (rq/convert.rs:17-44): polynomials of ciphertexts [first, first+n) -> power basis
+ * (if the batch is NTT) -> packed bytes; host_out receives n*parts blobs of packed_bytes each. */
+int fhe_b200_batch_pack(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint8_t* host_out, void* stream);
+/* TryConvertFrom<&Rq> for Poly<PowerBasis|Ntt> (rq/convert.rs:100-131): unpack n*parts blobs into ciphertexts
+ * [first, first+n) of `b`; when `b` is an NTT batch the rows are forward-transformed afterwards (as
+ * `p.into_ntt()` does).  The whole batch must be filled with one call per disjoint range before it is used. */
+int fhe_b200_batch_unpack(fhe_b200_batch* b, uint32_t first, uint32_t n, const uint8_t* host_in, void* stream);
+
 int fhe_b200_sync(void* stream);
 /* kernels launched by this library in the calling process so far (bench.py "gpu_launches") */
 uint64_t fhe_b200_launch_count(void);

@@ -592,6 +592,63 @@ class Poly:
         return [self.ctx.rns.lift([int(x) for x in self.c[:, j]]) for j in range(self.ctx.degree)]
 
 
+def transcode_to_bytes(a: Sequence[int], nbits: int) -> bytes:
+    """fhe_util::transcode_to_bytes, fhe-util/src/lib.rs:71-108 (LSB-first bit stream)."""
+    mask = (1 << nbits) - 1
+    cur, have, out = 0, 0, bytearray()
+    for v in a:
+        cur |= (int(v) & mask) << have
+        have += nbits
+        while have >= 8:
+            out.append(cur & 0xFF)
+            cur >>= 8
+            have -= 8
+    if have > 0:
+        out.append(cur & 0xFF)
+    return bytes(out)
+
+
+def transcode_from_bytes(b: bytes, nbits: int) -> List[int]:
+    """fhe_util::transcode_from_bytes, fhe-util/src/lib.rs:112-146."""
+    mask = (1 << nbits) - 1
+    cur, have, out = 0, 0, []
+    for byte in b:
+        cur |= byte << have
+        have += 8
+        while have >= nbits:
+            out.append(cur & mask)
+            cur >>= nbits
+            have -= nbits
+    if have > 0:
+        out.append(cur)
+    return out
+
+
+def poly_to_rq_coefficients(p: Poly) -> bytes:
+    """`Rq::from(&Poly).coefficients`, rq/convert.rs:17-44: always power basis, per-limb serialize_vec (zq/mod.rs:783)."""
+    q = p.copy()
+    if q.rep != POWER_BASIS:
+        q.into_power_basis()
+    out = b""
+    for i, m in enumerate(q.ctx.moduli):
+        out += transcode_to_bytes(q.c[i], (m - 1).bit_length())
+    return out
+
+
+def poly_from_rq_coefficients(ctx: Context, blob: bytes, rep: int) -> Poly:
+    """TryConvertFrom<&Rq> for Poly<PowerBasis|Ntt>, rq/convert.rs:46-131."""
+    n, idx, rows = ctx.degree, 0, []
+    for m in ctx.moduli:
+        nb = (m - 1).bit_length()
+        size = nb * n // 8
+        rows.append(transcode_from_bytes(blob[idx: idx + size], nb)[:n])
+        idx += size
+    if idx != len(blob):
+        raise ValueError("InvalidCoefficientCount")
+    p = Poly(ctx, POWER_BASIS, np.array(rows, dtype=np.uint64))
+    return p if rep == POWER_BASIS else p.into_ntt()
+
+
 def lazy_constant_ntt(row: np.ndarray, ctx: Context) -> Poly:
     """create_constant_ntt_polynomial_with_lazy_coefficients_and_variable_time,
     rq/mod.rs:563-586: values in [0,4q_j)."""

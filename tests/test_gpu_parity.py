@@ -365,3 +365,31 @@ def test_full_size_set_c(oracle, F):
     S = A + B
     S -= B
     assert (S.to_host() == a).all()
+
+
+@pytest.mark.parametrize("degree,sizes", [(16, [62, 62, 62]), (64, [50, 36, 20]), (4096, [62, 62])])
+def test_wire_format(oracle, F, degree, sizes):
+    """From<&Poly> for Rq / TryConvertFrom<&Rq> (rq/convert.rs:17-131): bit-packed power-basis coefficients"""
+    t = 1153 if degree < 4096 else 1032193
+    opar, gpar, rng = make_pair(oracle, F, degree, len(sizes), t, 7, sizes)
+    ctx = opar.context_at_level(0)
+    x = rand_ct(oracle, opar, rng, 3)
+    X = F.Ciphertext.from_host(gpar, x)                     # NTT batch
+    blobs = X.to_packed()
+    assert blobs.shape[2] == sum((q - 1).bit_length() * degree // 8 for q in ctx.moduli)
+    for c in range(3):
+        for p in range(2):
+            exp = oracle.poly_to_rq_coefficients(oracle.Poly(ctx, oracle.NTT, x[c, p]))
+            assert blobs[c, p].tobytes() == exp
+    Y = F.Ciphertext.from_packed(gpar, blobs, repr=F.NTT)
+    assert (Y.to_host() == x).all()
+    # power-basis batch: packing is the plain transcode of the stored words
+    Z = F.Ciphertext.from_host(gpar, x, repr=F.POWER_BASIS)
+    zb = Z.to_packed()
+    for c in range(3):
+        for p in range(2):
+            assert zb[c, p].tobytes() == oracle.poly_to_rq_coefficients(oracle.Poly(ctx, oracle.POWER_BASIS, x[c, p]))
+    W = F.Ciphertext.from_packed(gpar, zb, repr=F.POWER_BASIS)
+    assert (W.to_host() == x).all()
+    with pytest.raises(F.FheError):
+        F.Ciphertext.from_packed(gpar, zb[:, :, :-1], repr=F.NTT)

@@ -309,3 +309,24 @@ def test_leveled_keys(oracle):
     rk = oracle.RelinearizationKey(sk, rng, ciphertext_level=1, key_level=0)
     ct = rk.relinearizes(cta.mul(ctb))
     assert ct.level == 1 and (sk.decrypt(ct) == _negacyclic(a, b, 1153)).all()
+
+
+def test_transcode_roundtrip(oracle):
+    """fhe-util/src/lib.rs:323-372: transcode self-consistency, known 4-bit round trip, empty input"""
+    rnd = random.Random(9)
+    for size in (1, 2, 7, 8, 33, 100):
+        vals = [rnd.randrange(1 << 64) for _ in range(size)]
+        for nbits in (1, 4, 7, 8, 13, 36, 49, 61, 62):
+            masked = [v & ((1 << nbits) - 1) for v in vals]
+            b = oracle.transcode_to_bytes(masked, nbits)
+            assert len(b) == -(-size * nbits // 8)
+            assert oracle.transcode_from_bytes(b, nbits)[:size] == masked
+    assert oracle.transcode_from_bytes(oracle.transcode_to_bytes([1, 2, 3, 4, 5, 6, 7, 8], 4), 4) == [1, 2, 3, 4, 5, 6, 7, 8]
+    assert oracle.transcode_to_bytes([1, 2, 3, 4], 4) == bytes([0x21, 0x43])      # LSB-first nibbles
+    assert oracle.transcode_to_bytes([], 8) == b"" and oracle.transcode_from_bytes(b"", 8) == []
+    # Rq coefficients blob of a polynomial round-trips through both representations
+    ctx = oracle.Context(NFL_62[:2], 16)
+    p = oracle.Poly.random(ctx, oracle.NTT, np.random.default_rng(5))
+    blob = oracle.poly_to_rq_coefficients(p)
+    assert len(blob) == 2 * 62 * 16 // 8
+    assert (oracle.poly_from_rq_coefficients(ctx, blob, oracle.NTT).c == p.c).all()
