@@ -314,6 +314,14 @@ class Ciphertext:
         check(_capi.lib().fhe_b200_mul(self._h, rhs._h, out._h, self.stream))
         return out
 
+    def mul_plain(self, poly_ntt: np.ndarray) -> "Ciphertext":
+        """Ciphertext *= &Plaintext (ops/mod.rs:229-238), in place.  poly_ntt: the plaintext's `poly_ntt` words,
+        [limbs][N] (shared by the batch) or [count][limbs][N] (one plaintext per ciphertext)."""
+        w = np.ascontiguousarray(poly_ntt, dtype=np.uint64)
+        n = 1 if w.ndim == 2 else w.shape[0]
+        check(_capi.lib().fhe_b200_mul_plain(self._h, _ptr(w), n, self.stream))
+        return self
+
     def switch_down(self) -> "Ciphertext":
         """Ciphertext::switch_down (ciphertext.rs:148-161), in place."""
         check(_capi.lib().fhe_b200_switch_down(self._h, self.stream))
@@ -415,6 +423,51 @@ class EvaluationKey:
 
     def supports_column_rotation_by(self, i: int) -> bool:
         return pow(3, i, 2 * self.par.degree()) in self.gk
+
+    def supports_inner_sum(self) -> bool:  # evaluation_key.rs:40-53
+        n = self.par.degree()
+        i, ok = 1, self.supports_row_rotation()
+        while i < n // 2:
+            ok = ok and self.supports_column_rotation_by(i)
+            i *= 2
+        return ok
+
+    def computes_inner_sum(self, ct: Ciphertext) -> Ciphertext:
+        """EvaluationKey::computes_inner_sum (evaluation_key.rs:56-100)."""
+        if not self.supports_inner_sum():
+            raise FheError(_capi.INVALID_ARGUMENT, "EvaluationKeyError: inner sum not supported by this key")
+        out = ct.clone()
+        i = 1
+        while i < self.par.degree() // 2:
+            out += self.gk[pow(3, i, 2 * self.par.degree())].relinearize(out)
+            i *= 2
+        out += self.gk[2 * self.par.degree() - 1].relinearize(out)
+        return out
+
+    def expands(self, ct: Ciphertext, size: int, monomials: Sequence[np.ndarray]):
+        """EvaluationKey::expands (evaluation_key.rs:192-256), oblivious expansion of eprint 2019/1483.
+        monomials[l]: NTT words [limbs][N] of -x^(N - 2^l) (evaluation_key.rs:465-474)."""
+        n = self.par.degree()
+        if size == 0 or size > n:
+            raise FheError(_capi.INVALID_ARGUMENT, "EvaluationKeyError: invalid expansion size")
+        level = (size - 1).bit_length()
+        out = [None] * (1 << level)
+        out[0] = ct.clone()
+        for l in range(level):
+            gk = self.gk.get((n >> l) + 1)
+            if gk is None or l >= len(monomials):
+                raise FheError(_capi.INVALID_ARGUMENT, "EvaluationKeyError: expansion not supported by this key")
+            step = 1 << l
+            for i in range(step):
+                sub = gk.relinearize(out[i])
+                j = step | i
+                if j < size:
+                    tgt = out[i].clone()
+                    tgt -= sub
+                    tgt.mul_plain(monomials[l])
+                    out[j] = tgt
+                out[i] += sub
+        return out[:size]
 
     def rotates_rows(self, ct: Ciphertext) -> Ciphertext:  # evaluation_key.rs:110-126
         e = 2 * self.par.degree() - 1

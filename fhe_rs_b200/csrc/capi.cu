@@ -646,6 +646,24 @@ int fhe_b200_add(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream) { ret
 int fhe_b200_sub(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream) { return ew(EW_SUB, a, b, stream); }
 int fhe_b200_neg(fhe_b200_batch* a, void* stream) { return ew(EW_NEG, a, nullptr, stream); }
 
+int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, void* stream) {
+  API_BEGIN
+  REQUIRE(a && host_polys, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE(n_polys == 1 || n_polys == a->count, FHE_B200_INVALID_ARGUMENT, "n_polys must be 1 or the batch size");
+  need_repr(a, FHE_B200_NTT);
+  const fhe_b200_params* par = a->par;
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(st);
+  const size_t words = ((size_t)n_polys * a->limbs) << par->logn;
+  u64* pt = ws.words(words);
+  FHE_CUDA(cudaMemcpyAsync(pt, host_polys, words * sizeof(u64), cudaMemcpyHostToDevice, st));
+  launch_mul_plain(a->d, pt, a->count, a->parts, n_polys, ids_of(a), par->d_limbs, par->logn, st);
+  FHE_CUDA(cudaGetLastError());
+  FHE_CUDA(cudaStreamSynchronize(st));   // host_polys may be pageable: do not return before it has been read
+  API_END
+}
+
 int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batch* out3, void* stream) {
   API_BEGIN
   REQUIRE(a && b && out3, FHE_B200_INVALID_ARGUMENT, "null argument");

@@ -36,6 +36,10 @@ enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2 };
 void launch_ew(EwOp op, u64* a, const u64* b, size_t n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
                cudaStream_t st);
 
+// a[ct][part][limb][:] *= pt[ct % n_pt][limb][:]   (Modulus::mul_vec, zq/mod.rs:332)
+void launch_mul_plain(u64* a, const u64* pt, u32 cts, u32 parts, u32 n_pt, const RowIds& ids, const LimbDev* limbs,
+                      u32 logn, cudaStream_t st);
+
 // tensor product of two 2-part ciphertexts over the multiplication basis (mul.rs:198-201).
 // a,b: [ct][2][L][N] (common-prefix limbs, NTT); xa,xb: [ct][2][E][N] (extension limbs, NTT);
 // out: [ct][3][K][N].

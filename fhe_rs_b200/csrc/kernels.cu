@@ -42,6 +42,27 @@ __global__ void ew_kernel(EwArgs A) {
   *reinterpret_cast<ulonglong2*>(A.a + i) = x;
 }
 
+// ------------------------------------------------------------------ ciphertext x plaintext polynomial
+struct MulPlainArgs {
+  u64* a;
+  const u64* pt;
+  u32 cts, parts, n_pt, logn, limbs_per_poly;
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+__global__ void mul_plain_kernel(MulPlainArgs A) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = ((size_t)A.cts * A.parts * A.limbs_per_poly) << A.logn;
+  if (idx >= total) return;
+  const u32 c = idx & ((1u << A.logn) - 1);
+  const size_t row = idx >> A.logn;
+  const u32 limb = row % A.limbs_per_poly;
+  const u32 ct = (u32)(row / ((size_t)A.limbs_per_poly * A.parts));
+  const LimbDev& M = A.limbs[A.ids[limb]];
+  const u64 w = A.pt[((((size_t)(ct % A.n_pt)) * A.limbs_per_poly + limb) << A.logn) + c];
+  A.a[idx] = mulmod_limb(A.a[idx], w, M);
+}
+
 // ------------------------------------------------------------------ tensor
 struct TensorArgs {
   const u64 *a, *b, *xa, *xb;
@@ -476,6 +497,18 @@ void launch_ew(EwOp op, u64* a, const u64* b, size_t n_rows, const RowIds& ids, 
   if (op == EW_ADD) ew_kernel<EW_ADD><<<(unsigned)blocks, threads, 0, st>>>(A);
   else if (op == EW_SUB) ew_kernel<EW_SUB><<<(unsigned)blocks, threads, 0, st>>>(A);
   else ew_kernel<EW_NEG><<<(unsigned)blocks, threads, 0, st>>>(A);
+  g_launches++;
+}
+
+void launch_mul_plain(u64* a, const u64* pt, u32 cts, u32 parts, u32 n_pt, const RowIds& ids, const LimbDev* limbs,
+                      u32 logn, cudaStream_t st) {
+  MulPlainArgs A;
+  A.a = a; A.pt = pt; A.cts = cts; A.parts = parts; A.n_pt = n_pt; A.logn = logn;
+  A.limbs_per_poly = ids.limbs_per_poly; A.limbs = limbs;
+  copy_ids(A.ids, ids);
+  size_t total = ((size_t)cts * parts * ids.limbs_per_poly) << logn;
+  if (!total) return;
+  mul_plain_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
   g_launches++;
 }
 

@@ -130,6 +130,10 @@ int fhe_b200_ntt_backward(fhe_b200_batch* b, void* stream);
 int fhe_b200_add(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream);
 int fhe_b200_sub(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream);
 int fhe_b200_neg(fhe_b200_batch* a, void* stream);
+/* Ciphertext *= &Plaintext (bfv/ops/mod.rs:229-238; Poly<Ntt> *= &Poly<Ntt>, rq/ops.rs:174): every part of every
+ * ciphertext is multiplied coefficient-wise by an NTT-domain polynomial.  host_polys holds n_polys polynomials of
+ * [limbs][N] words (Plaintext::poly_ntt, or a monomial of EvaluationKey::expands); n_polys is 1 (shared) or count. */
+int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, void* stream);
 /* &Ciphertext * &Ciphertext, 2 parts x 2 parts -> 3 parts (bfv/ops/mod.rs:259-358) */
 int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batch* out3, void* stream);
 /* RelinearizationKey::relinearizes: (c0,c1,c2) -> (c0,c1) (keys/relinearization_key.rs:70-103) */

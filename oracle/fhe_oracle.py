@@ -1097,6 +1097,43 @@ class GaloisKey:
         return Ciphertext(ct.par, [c0, c1], self.ksk.ciphertext_level)
 
 
+def computes_inner_sum(par: BfvParameters, gks: dict, ct: Ciphertext) -> Ciphertext:
+    """EvaluationKey::computes_inner_sum, evaluation_key.rs:56-100 (gks: exponent -> GaloisKey)."""
+    out = ct.copy()
+    i = 1
+    while i < par.degree // 2:
+        out = out.add(gks[pow(3, i, 2 * par.degree)].relinearize(out))
+        i *= 2
+    return out.add(gks[2 * par.degree - 1].relinearize(out))
+
+
+def expansion_monomial(par: BfvParameters, l: int, level: int = 0) -> Poly:
+    """evaluation_key.rs:465-474: -x^(N - 2^l) as Poly<NttShoup>."""
+    v = np.zeros(par.degree, np.int64)
+    v[par.degree - (1 << l)] = -1
+    return Poly.from_i64(par.context_at_level(level), v).into_ntt_shoup()
+
+
+def expands(par: BfvParameters, gks: dict, ct: Ciphertext, size: int) -> List[Ciphertext]:
+    """EvaluationKey::expands, evaluation_key.rs:192-256."""
+    level = (size - 1).bit_length()
+    out: List[Optional[Ciphertext]] = [None] * (1 << level)
+    out[0] = ct.copy()
+    for l in range(level):
+        mono = expansion_monomial(par, l, ct.level)
+        gk = gks[(par.degree >> l) + 1]
+        step = 1 << l
+        for i in range(step):
+            sub = gk.relinearize(out[i])
+            j = step | i
+            if j < size:
+                tgt = out[i].sub(sub)
+                tgt.c = [p.imul(mono) for p in tgt.c]
+                out[j] = tgt
+            out[i] = out[i].add(sub)
+    return out[:size]
+
+
 def rotation_exponent(par: BfvParameters, i: int) -> int:
     """column rotation by i <-> 3^i mod 2N (evaluation_key.rs:278-286); row swap <-> 2N-1 (:118)."""
     return pow(3, i, 2 * par.degree)

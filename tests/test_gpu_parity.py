@@ -393,3 +393,43 @@ def test_wire_format(oracle, F, degree, sizes):
     assert (W.to_host() == x).all()
     with pytest.raises(F.FheError):
         F.Ciphertext.from_packed(gpar, zb[:, :, :-1], repr=F.NTT)
+
+
+def test_mul_plain_inner_sum_expand(oracle, F):
+    """Ciphertext * Plaintext (ops/mod.rs:229-238), EvaluationKey::computes_inner_sum (evaluation_key.rs:56-100)
+    and EvaluationKey::expands (:192-256) -- the PIR examples' loops, built from the same kernels"""
+    degree, t = 16, 1153
+    opar, gpar, rng = make_pair(oracle, F, degree, 3, t, 123)
+    exps = sorted({pow(3, 1 << k, 2 * degree) for k in range(3)} | {2 * degree - 1} | {(degree >> l) + 1 for l in range(2)})
+    sk, ork, grk, ogk, ggk = _keys(oracle, F, opar, gpar, rng, exps)
+    vals = rng.integers(0, t, size=(2, degree))
+    octs = [sk.encrypt(oracle.simd_encode(opar, v), 0, rng) for v in vals]
+    X = F.Ciphertext.from_host(gpar, np.stack([c.to_array() for c in octs]))
+    # ct * pt
+    pt = oracle.plaintext_to_poly(opar, rng.integers(0, t, degree), 0)    # any NTT-domain polynomial of the level
+    got = X.clone().mul_plain(pt.c).to_host()
+    for i in range(2):
+        assert (got[i] == np.stack([p.mul(pt).c for p in octs[i].c])).all()
+    per_ct = np.stack([oracle.Poly.random(opar.context_at_level(0), oracle.NTT, rng).c for _ in range(2)])
+    got = X.clone().mul_plain(per_ct).to_host()
+    for i in range(2):
+        w = oracle.Poly(opar.context_at_level(0), oracle.NTT, per_ct[i])
+        assert (got[i] == np.stack([p.mul(w).c for p in octs[i].c])).all()
+    # inner sum
+    ek = F.EvaluationKey(gpar)
+    for e in exps:
+        ek.add_galois_key(ggk[e])
+    assert ek.supports_inner_sum()
+    got = ek.computes_inner_sum(X).to_host()
+    for i in range(2):
+        exp = oracle.computes_inner_sum(opar, ogk, octs[i])
+        assert (got[i] == exp.to_array()).all()
+        dec = oracle.simd_decode(opar, sk.decrypt(oracle.Ciphertext.from_array(opar, got[i], 0)))
+        assert (dec == np.full(degree, int(vals[i].sum()) % t, dtype=np.uint64)).all()
+    # oblivious expansion to 4 ciphertexts
+    monos = [oracle.expansion_monomial(opar, l).c for l in range(2)]
+    outs = ek.expands(X, 4, monos)
+    for i in range(2):
+        exp = oracle.expands(opar, ogk, octs[i], 4)
+        for k in range(4):
+            assert (outs[k].to_host()[i] == exp[k].to_array()).all()

@@ -330,3 +330,25 @@ def test_transcode_roundtrip(oracle):
     blob = oracle.poly_to_rq_coefficients(p)
     assert len(blob) == 2 * 62 * 16 // 8
     assert (oracle.poly_from_rq_coefficients(ctx, blob, oracle.NTT).c == p.c).all()
+
+
+def test_inner_sum_and_expansion_semantics(oracle):
+    """evaluation_key.rs tests (:600-760): inner sum puts the slot sum in every slot; oblivious expansion of
+    Enc(sum_k m_k x^k) to `size` ciphertexts gives Enc(2^level * m_k) (constant polynomials)."""
+    degree, t = 16, 1153
+    rng = np.random.default_rng(77)
+    par = oracle.BfvParameters(degree, t, moduli_sizes=[62] * 3)
+    sk = oracle.SecretKey(par, rng)
+    exps = sorted({pow(3, 1 << k, 2 * degree) for k in range(3)} | {2 * degree - 1} | {(degree >> l) + 1 for l in range(2)})
+    gks = {e: oracle.GaloisKey(sk, e, rng) for e in exps}
+    v = rng.integers(0, t, degree)
+    ct = sk.encrypt(oracle.simd_encode(par, v), 0, rng)
+    dec = oracle.simd_decode(par, sk.decrypt(oracle.computes_inner_sum(par, gks, ct)))
+    assert (dec == np.full(degree, int(v.sum()) % t, dtype=np.uint64)).all()
+    m = np.zeros(degree, dtype=np.int64)
+    m[:4] = rng.integers(0, t, 4)      # the query polynomial carries one value per expanded ciphertext
+    ct = sk.encrypt(m, 0, rng)
+    outs = oracle.expands(par, gks, ct, 4)
+    for k in range(4):
+        d = sk.decrypt(outs[k])
+        assert int(d[0]) == (4 * int(m[k])) % t and not d[1:].any()
