@@ -1,6 +1,7 @@
 // C ABI of the engine (include/fhe_b200.h): parameter precompute + upload, device batches,
 // key material, and the batched homomorphic operations built from the kernels of
 // ntt.cu / kernels.cu.  No CPU fallback: compute entry points require a CUDA device.
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <map>
@@ -240,8 +241,14 @@ void key_switch_core(const fhe_b200_params* par, const fhe_b200_ksk* k, const u6
   const LevelData& kl = par->level(k->ksk_level);
   const u32 L = k->n_dig, Lk = k->Lk;
   u64* inter = ws.words(((size_t)cts * L * Lk) << par->logn);
-  // digit broadcast + reduction modulo q_j on load (rq/mod.rs:563-586), then NTT of every (digit, limb) row
-  launch_ntt(c2, inter, cts * L * Lk, kl.ctx_ids, par->d_limbs, par->logn, false, Lk, true, st);
+  // digit broadcast (rq/mod.rs:563-586), then NTT of every (digit, limb) row.  The reference lazily reduces the
+  // digit modulo q_j before its lazy transform; the forward butterflies accept any input below 4*q_j, so the
+  // reduction on load is only needed when a digit (< max q_i) can reach 4 * min q_j (mixed modulus sizes).
+  u64 qmax = 0, qmin = ~0ull;
+  for (u32 i = 0; i < L; i++) qmax = std::max(qmax, par->moduli[i]);
+  for (u32 j = 0; j < Lk; j++) qmin = std::min(qmin, par->moduli[j]);
+  const bool reduce = qmax > 4 * qmin - 1 || qmin < (1ull << 8);
+  launch_ntt(c2, inter, cts * L * Lk, kl.ctx_ids, par->d_limbs, par->logn, false, Lk, reduce, st);
   launch_ksmac(inter, k->k0, k->k1, base0, base1, out0, out1, cts, L, Lk, out_ct_rows, kl.ctx_ids, par->d_limbs,
                par->logn, st);
 }

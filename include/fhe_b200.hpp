@@ -139,8 +139,34 @@ class Ciphertext {
     check(fhe_b200_mul(h_, rhs.h_, out.h_, stream_));
     return out;
   }
+  // Ciphertext *= &Plaintext (bfv/ops/mod.rs:229): poly_ntt = [limbs][N] words shared by the batch
+  Ciphertext& mul_plain(const std::vector<uint64_t>& poly_ntt) {
+    check(fhe_b200_mul_plain(h_, poly_ntt.data(), 1, stream_));
+    return *this;
+  }
   // Ciphertext::switch_down (bfv/ciphertext.rs:148)
   void switch_down() { check(fhe_b200_switch_down(h_, stream_)); }
+  // Rq.coefficients of every polynomial (rq/convert.rs:17-44): count*parts blobs of packed_bytes() each
+  size_t packed_bytes() const {
+    size_t n = 0;
+    check(fhe_b200_poly_packed_bytes(par_->handle(), level(), &n));
+    return n;
+  }
+  std::vector<uint8_t> to_packed() const {
+    std::vector<uint8_t> out((size_t)count() * len() * packed_bytes());
+    check(fhe_b200_batch_pack(h_, 0, count(), out.data(), stream_));
+    return out;
+  }
+  // TryConvertFrom<&Rq> for Poly<Ntt> (rq/convert.rs:116-131) for every polynomial of the batch
+  static Ciphertext from_packed(std::shared_ptr<BfvParameters> par, const std::vector<uint8_t>& blobs, uint32_t count,
+                                uint32_t parts = 2, uint32_t level = 0, Representation r = Representation::Ntt) {
+    Ciphertext ct(std::move(par), count, parts, level, r);
+    if (blobs.size() != (size_t)count * parts * ct.packed_bytes())
+      throw Error(FHE_B200_INVALID_ARGUMENT, "InvalidCoefficientCount");
+    check(fhe_b200_batch_unpack(ct.h_, 0, count, blobs.data(), ct.stream_));
+    check(fhe_b200_sync(ct.stream_));
+    return ct;
+  }
 
   fhe_b200_batch* handle() const { return h_; }
   const std::shared_ptr<BfvParameters>& par() const { return par_; }

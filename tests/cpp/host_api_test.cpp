@@ -45,6 +45,8 @@ int main(int argc, char** argv) {
     if (P1 != P2) { printf("FAIL multiply != mul + relinearizes\n"); return 1; }
     // multiplication is commutative bit for bit (canonical residues)
     if (m.multiply(B, A).to_host() != P1) { printf("FAIL commutativity\n"); return 1; }
+    // wire format round trip (Rq.coefficients blobs)
+    if (Ciphertext::from_packed(par, A.to_packed(), count).to_host() != wa) { printf("FAIL wire round trip\n"); return 1; }
     // error behaviour
     try {
       m.multiply(C3, B);
