@@ -601,23 +601,10 @@ int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uin
   k->par = p; k->ct_level = ciphertext_level; k->ksk_level = ksk_level; k->n_dig = n_digits; k->Lk = kl.L;
   size_t bytes = ((size_t)n_digits * kl.L << p->logn) * sizeof(u64);
   k->k0 = k->k1 = nullptr;
-  // the device inner product consumes the key words in split31 form (zq.cuh AccCS4); every word must be a
-  // canonical residue (< 2^62), as the reference's Poly<NttShoup> guarantees
-  const size_t words = bytes / sizeof(u64);
-  std::vector<u64> tmp0(words), tmp1(words);
-  for (size_t w = 0; w < words; w++) {
-    REQUIRE(((c0[w] | c1[w]) >> 62) == 0, FHE_B200_INVALID_ARGUMENT, "key word is not a reduced residue");
-    tmp0[w] = split31(c0[w]);
-    tmp1[w] = split31(c1[w]);
-  }
   FHE_CUDA(cudaMalloc(&k->k0, bytes));
-  if (cudaMalloc(&k->k1, bytes) != cudaSuccess) {
-    cudaFree(k->k0);
-    cudaGetLastError();
-    throw FheError(FHE_B200_OUT_OF_MEMORY, "cudaMalloc failed for the key");
-  }
-  FHE_CUDA(cudaMemcpy(k->k0, tmp0.data(), bytes, cudaMemcpyHostToDevice));
-  FHE_CUDA(cudaMemcpy(k->k1, tmp1.data(), bytes, cudaMemcpyHostToDevice));
+  FHE_CUDA(cudaMalloc(&k->k1, bytes));
+  FHE_CUDA(cudaMemcpy(k->k0, c0, bytes, cudaMemcpyHostToDevice));
+  FHE_CUDA(cudaMemcpy(k->k1, c1, bytes, cudaMemcpyHostToDevice));
   params_retain(p);
   *out = k.release();
   API_END

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   for (u32 i = 0; i < nf; i++) s_r[i * TC + cc] = src[((size_t)i << A.logn) + cc];
   for (u32 jj = 0; jj < n_out4; jj++)
     for (u32 ii = cc; ii < nf; ii += TC)
-      s_omega[ii * n_out4 + jj] = jj < n_out ? split31(S.omega[(size_t)(A.start + jj) * nf + ii]) : 0;
+      s_omega[ii * n_out4 + jj] = jj < n_out ? S.omega[(size_t)(A.start + jj) * nf + ii] : 0;
   for (u32 i = cc; i < n_out4; i += TC) s_gamma[i] = i < n_out ? S.gamma[A.start + i] : 0;
   for (u32 i = cc; i < nf; i += TC) {
     s_tgl[i] = S.tgar_lo[i];
@@ -240,28 +240,17 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   // outputs (:316-351): y_j = (-(v mod q_j) * gamma_j +/- w + sum_i r_i * omega_ji) mod q_j, four limbs at a time
   for (u32 j0 = 0; j0 < n_out; j0 += 4) {
     Acc192 acc[4];
-    AccCS4 cs[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      acc[k].clear();
-      cs[k].clear();
-    }
+    for (int k = 0; k < 4; k++) acc[k].clear();
     const ulonglong2* om = reinterpret_cast<const ulonglong2*>(s_omega + j0);
-    for (u32 i0 = 0; i0 < nf; i0 += 4) {   // four source limbs per carry-save window
-#pragma unroll
-      for (u32 d = 0; d < 4; d++) {
-        const u32 i = i0 + d;
-        if (i < nf) {
-          const u64 r = split31(s_r[i * TC + cc]);
-          const ulonglong2 o0 = om[(size_t)i * (n_out4 / 2)], o1 = om[(size_t)i * (n_out4 / 2) + 1];
-          cs[0].mac(r, o0.x);
-          cs[1].mac(r, o0.y);
-          cs[2].mac(r, o1.x);
-          cs[3].mac(r, o1.y);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) cs[k].flush(acc[k].lo, acc[k].mid, acc[k].hi);
+#pragma unroll 2
+    for (u32 i = 0; i < nf; i++) {
+      const u64 r = s_r[i * TC + cc];
+      const ulonglong2 o0 = om[(size_t)i * (n_out4 / 2)], o1 = om[(size_t)i * (n_out4 / 2) + 1];
+      acc[0].mac(r, o0.x);
+      acc[1].mac(r, o0.y);
+      acc[2].mac(r, o1.x);
+      acc[3].mac(r, o1.y);
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -374,33 +363,26 @@ __global__ void ksmac_kernel(KsMacArgs A) {
   u32 ct = row % A.cts, j = row / A.cts;
   const LimbDev& M = A.limbs[A.ids[j]];
   Acc192 a0, a1;
-  AccCS4 s0, s1;
   a0.clear();
   a1.clear();
-  s0.clear();
-  s1.clear();
   const u64* t_ptr = A.inter + ((((size_t)ct * A.n_dig) * A.Lk + j) << A.logn) + c;
-  const u64* k0_ptr = A.k0 + ((size_t)j << A.logn) + c;   // key words are stored in split31 form
+  const u64* k0_ptr = A.k0 + ((size_t)j << A.logn) + c;
   const u64* k1_ptr = A.k1 + ((size_t)j << A.logn) + c;
   const size_t dstride = (size_t)A.Lk << A.logn;
-  for (u32 i0 = 0; i0 < A.n_dig; i0 += 4) {   // four digits per carry-save window: twelve independent loads in flight
-    u64 t[4], x[4], y[4];
-#pragma unroll
-    for (u32 d = 0; d < 4; d++) {
-      const bool ok = i0 + d < A.n_dig;
-      const size_t off = (size_t)(i0 + d) * dstride;
-      t[d] = ok ? t_ptr[off] : 0;
-      x[d] = ok ? __ldg(k0_ptr + off) : 0;
-      y[d] = ok ? __ldg(k1_ptr + off) : 0;
-    }
-#pragma unroll
-    for (u32 d = 0; d < 4; d++) {
-      const u64 ts = split31(t[d]);
-      s0.mac(ts, x[d]);
-      s1.mac(ts, y[d]);
-    }
-    s0.flush(a0.lo, a0.mid, a0.hi);
-    s1.flush(a1.lo, a1.mid, a1.hi);
+  u32 i = 0;
+  for (; i + 2 <= A.n_dig; i += 2) {   // two digits per trip: six independent loads in flight
+    const u64 t0 = t_ptr[(size_t)i * dstride], t1 = t_ptr[(size_t)(i + 1) * dstride];
+    const u64 x0 = __ldg(k0_ptr + (size_t)i * dstride), x1 = __ldg(k0_ptr + (size_t)(i + 1) * dstride);
+    const u64 y0 = __ldg(k1_ptr + (size_t)i * dstride), y1 = __ldg(k1_ptr + (size_t)(i + 1) * dstride);
+    a0.mac(t0, x0);
+    a1.mac(t0, y0);
+    a0.mac(t1, x1);
+    a1.mac(t1, y1);
+  }
+  if (i < A.n_dig) {
+    const u64 t0 = t_ptr[(size_t)i * dstride];
+    a0.mac(t0, __ldg(k0_ptr + (size_t)i * dstride));
+    a1.mac(t0, __ldg(k1_ptr + (size_t)i * dstride));
   }
   const size_t o = (((size_t)ct * A.out_ct_rows + j) << A.logn) + c;
   if (A.base0) a0.add64(A.base0[o]);

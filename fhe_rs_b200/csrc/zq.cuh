@@ -293,41 +293,6 @@ struct Acc192 {
   }
 };
 
-// Carry-save companion of Acc192 for sums of products of operands < 2^62.  Both operands are split at bit 31
-// (x = x1*2^31 + x0), so each of the four partial products is < 2^62 and four of them fit a 64-bit column: the
-// multiply-accumulates are plain IMAD.WIDE with the column as addend (the FMA pipe does the additions, no carry
-// instructions on the issue port), and the columns are folded into the 192-bit accumulator every four terms.
-// Constants are stored pre-split: split31(w) = (w >> 31) << 32 | (w & (2^31 - 1)).
-__host__ __device__ __forceinline__ u64 split31(u64 w) { return ((w >> 31) << 32) | (w & 0x7fffffffull); }
-struct AccCS4 {
-  u64 c0, c1a, c1b, c2;
-  __device__ __forceinline__ void clear() { c0 = c1a = c1b = c2 = 0; }
-  // a = split31 form of the variable operand, b = split31 form of the constant
-  __device__ __forceinline__ void mac(u64 a, u64 b) {
-    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    c0 += (u64)a0 * b0;
-    c1a += (u64)a0 * b1;
-    c1b += (u64)a1 * b0;
-    c2 += (u64)a1 * b1;
-  }
-  // acc += c0 + (c1a + c1b)*2^31 + c2*2^62 ; columns cleared
-  __device__ __forceinline__ void flush(u64& lo, u64& mid, u64& hi) {
-    typedef unsigned __int128 u128;
-    const u128 m = (u128)c1a + c1b;                                   // < 2^65
-    const u128 s = (u128)c0 + (m << 31) + ((u128)(c2 << 62));         // low 128 bits of everything below 2^126.. (c2<<62 low word)
-    const u128 t = ((u128)(c2 >> 2)) << 64;                           // high word of c2*2^62
-    u128 low = ((u128)mid << 64) | lo;
-    const u128 r1 = low + s;
-    u64 carry = r1 < s;
-    const u128 r2 = r1 + t;
-    carry += r2 < t;
-    lo = (u64)r2;
-    mid = (u64)(r2 >> 64);
-    hi += carry;
-    c0 = c1a = c1b = c2 = 0;
-  }
-};
-
 // canonical residue of a 128-bit value
 __device__ __forceinline__ u64 reduce128_limb(u64 lo, u64 hi, const LimbDev& m) {
   if (m.sol_c) return csub(fold192_solinas(lo, hi, 0, (u32)m.sol_c), m.p);
