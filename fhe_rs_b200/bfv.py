@@ -19,7 +19,7 @@ import numpy as np
 from . import _capi
 from ._capi import NTT, POWER_BASIS, FheError, check
 
-__all__ = ["BfvParameters", "BfvParametersBuilder", "Ciphertext", "KeySwitchingKey", "RelinearizationKey",
+__all__ = ["BfvParameters", "BfvParametersBuilder", "Ciphertext", "KeySwitchingKey", "RelinearizationKey", "RGSWCiphertext",
            "GaloisKey", "EvaluationKey", "Multiplicator", "FheError", "NTT", "POWER_BASIS"]
 
 
@@ -369,6 +369,31 @@ class KeySwitchingKey:
         POWER_BASIS batch; returns the (c0, c1) pair as a 2-part NTT batch at the key level."""
         out = Ciphertext(self.par, p.count, 2, self.ksk_level, NTT, p.stream)
         check(_capi.lib().fhe_b200_key_switch(p._h, part, self._h, out._h, p.stream))
+        return out
+
+
+class RGSWCiphertext:
+    """fhe::bfv::RGSWCiphertext (bfv/rgsw_ciphertext.rs:20-24): two key-switching keys (for m and m*s)."""
+
+    def __init__(self, ksk0: KeySwitchingKey, ksk1: KeySwitchingKey):
+        if ksk0.ksk_level != ksk0.ciphertext_level or ksk1.ksk_level != ksk1.ciphertext_level \
+                or ksk0.ciphertext_level != ksk1.ciphertext_level:
+            raise FheError(_capi.INVALID_LEVEL, "RGSW key-switching keys must share one level")  # rgsw_ciphertext.rs:58-70
+        self.ksk0, self.ksk1 = ksk0, ksk1
+
+    @staticmethod
+    def from_arrays(par: BfvParameters, k0c0, k0c1, k1c0, k1c1, level: int = 0) -> "RGSWCiphertext":
+        return RGSWCiphertext(KeySwitchingKey(par, k0c0, k0c1, level, level), KeySwitchingKey(par, k1c0, k1c1, level, level))
+
+    def external_product(self, ct: Ciphertext) -> Ciphertext:
+        """&Ciphertext * &RGSWCiphertext (rgsw_ciphertext.rs:122-155): key-switch both parts, add."""
+        if ct.level != self.ksk0.ciphertext_level:
+            raise FheError(_capi.INVALID_LEVEL, "Ciphertext and RGSWCiphertext must have the same level")
+        if len(ct) != 2:
+            raise FheError(_capi.BAD_POLY_COUNT, "Ciphertext must have two parts")
+        pb = ct.clone().into_power_basis()
+        out = self.ksk0.key_switch(pb, part=0)
+        out += self.ksk1.key_switch(pb, part=1)
         return out
 
 

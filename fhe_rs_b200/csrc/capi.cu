@@ -214,7 +214,7 @@ struct Workspace {
 u32 chunk_size() {
   static u32 c = [] {
     const char* e = getenv("FHE_B200_CHUNK");
-    int v = e ? atoi(e) : 32;
+    int v = e ? atoi(e) : 64;
     return (u32)(v < 1 ? 1 : v);
   }();
   return c;
@@ -398,6 +398,10 @@ static int params_build(int device, uint32_t degree, const std::vector<u64>& mod
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
       unsigned long long thr = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      // scratch freed on one stream must not be handed to another stream through an inserted dependency: that
+      // serialises callers that pipeline chunks over several streams (bench.py e2e); let each stream keep its own
+      int off = 0;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
     }
   }
   for (size_t i = 0; i < p->primes.size(); i++) {

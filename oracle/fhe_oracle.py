@@ -1039,6 +1039,27 @@ class KeySwitchingKey:
         return np.stack([p.c for p in self.c0]), np.stack([p.c for p in self.c1])
 
 
+class RGSWCiphertext:
+    """bfv/rgsw_ciphertext.rs:20-155: encryption of a plaintext polynomial as two key-switching keys (m, m*s)."""
+
+    def __init__(self, sk: SecretKey, m_scaled_ntt: Poly, level: int, rng):
+        # FheEncrypter<Plaintext, RGSWCiphertext> for SecretKey (:93-120): m = pt.poly_ntt (unscaled message, NTT)
+        ctx = sk.par.context_at_level(level)
+        m = m_scaled_ntt.copy().into_power_basis()
+        m_s = sk.s_ntt(ctx).imul(m_scaled_ntt).into_power_basis()
+        self.ksk0 = KeySwitchingKey(sk, m, level, level, rng)
+        self.ksk1 = KeySwitchingKey(sk, m_s, level, level, rng)
+        self.level = level
+
+    def external_product(self, ct: Ciphertext) -> Ciphertext:  # :122-155
+        assert ct.level == self.level and len(ct.c) == 2
+        ct0 = ct.c[0].copy().into_power_basis()
+        ct1 = ct.c[1].copy().into_power_basis()
+        c0, c1 = self.ksk0.key_switch(ct0)
+        c0p, c1p = self.ksk1.key_switch(ct1)
+        return Ciphertext(ct.par, [c0.iadd(c0p), c1.iadd(c1p)], ct.level)
+
+
 def _post_key_switch(c0: Poly, c1: Poly, target: Context):
     """relinearization_key.rs:88-95 / galois_key.rs:69-76."""
     if c0.ctx != target:

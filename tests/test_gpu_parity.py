@@ -433,3 +433,19 @@ def test_mul_plain_inner_sum_expand(oracle, F):
         exp = oracle.expands(opar, ogk, octs[i], 4)
         for k in range(4):
             assert (outs[k].to_host()[i] == exp[k].to_array()).all()
+
+
+def test_rgsw_external_product(oracle, F):
+    """&Ciphertext * &RGSWCiphertext (rgsw_ciphertext.rs:122-155) through the key-switch primitive"""
+    degree, t = 64, 1153
+    opar, gpar, rng = make_pair(oracle, F, degree, 3, t, 321)
+    sk = oracle.SecretKey(opar, rng)
+    m2 = rng.integers(0, t, degree)
+    pt_ntt = oracle.Poly.from_u64(opar.context_at_level(0), m2.astype(np.uint64), oracle.NTT)
+    org = oracle.RGSWCiphertext(sk, pt_ntt, 0, rng)
+    grg = F.RGSWCiphertext.from_arrays(gpar, *org.ksk0.arrays(), *org.ksk1.arrays())
+    octs = [sk.encrypt(rng.integers(0, t, degree), 0, rng) for _ in range(3)]
+    X = F.Ciphertext.from_host(gpar, np.stack([c.to_array() for c in octs]))
+    got = grg.external_product(X).to_host()
+    for i in range(3):
+        assert (got[i] == org.external_product(octs[i]).to_array()).all()

@@ -352,3 +352,17 @@ def test_inner_sum_and_expansion_semantics(oracle):
     for k in range(4):
         d = sk.decrypt(outs[k])
         assert int(d[0]) == (4 * int(m[k])) % t and not d[1:].any()
+
+
+def test_rgsw_external_product(oracle):
+    """rgsw_ciphertext.rs tests (:200-245): Dec(ct * RGSW(m2)) == m1 (*) m2 (negacyclic product mod t)"""
+    degree, t = 16, 1153
+    rng = np.random.default_rng(88)
+    par = oracle.BfvParameters(degree, t, moduli_sizes=[62] * 3)
+    sk = oracle.SecretKey(par, rng)
+    m1, m2 = rng.integers(0, t, degree), rng.integers(0, t, degree)
+    ct = sk.encrypt(m1, 0, rng)
+    pt_ntt = oracle.Poly.from_u64(par.context_at_level(0), m2.astype(np.uint64), oracle.NTT)  # Plaintext.poly_ntt
+    rgsw = oracle.RGSWCiphertext(sk, pt_ntt, 0, rng)
+    out = rgsw.external_product(ct)
+    assert (sk.decrypt(out) == _negacyclic(m1, m2, t)).all()
