@@ -268,8 +268,8 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public host API (C ABI) with HOST buffers: every step uploads the step's
-    # operands from pinned host memory, multiplies, and downloads the products; chunks of 32 pairs alternate
-    # between two streams so that PCIe copies overlap the kernels of the other chunk
+    # operands from pinned host memory, multiplies, and downloads the products; chunks of 32 pairs rotate over
+    # several streams so that PCIe copies overlap the kernels of the other chunks
     Be = min(args.e2e_batch, B)
     ch = min(32, Be)
     Be -= Be % ch
@@ -280,13 +280,14 @@ def main():
     ha.copy_(torch.as_tensor(DevArray(A.device_ptr(), Be * wpc), device="cuda"))
     hb.copy_(torch.as_tensor(DevArray(Bt.device_ptr(), Be * wpc), device="cuda"))
     torch.cuda.synchronize()
-    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    n_slots = int(os.environ.get("FHE_BENCH_E2E_SLOTS", "3"))   # upload k+1 while k computes and k-1 downloads
+    streams = [torch.cuda.Stream() for _ in range(n_slots)]
     slots = [(F.Ciphertext(par, ch, 2), F.Ciphertext(par, ch, 2), F.Ciphertext(par, ch, 2)) for _ in streams]
 
     def e2e_step():
         for k in range(Be // ch):
-            st = streams[k % 2].cuda_stream
-            sa, sb, so = slots[k % 2]
+            st = streams[k % n_slots].cuda_stream
+            sa, sb, so = slots[k % n_slots]
             off = k * ch * wpc * 8
             check(L.fhe_b200_batch_upload(sa._h, 0, ch, ha.data_ptr() + off, st))
             check(L.fhe_b200_batch_upload(sb._h, 0, ch, hb.data_ptr() + off, st))

@@ -79,13 +79,22 @@ struct FastTile {
       const u32 root0 = COLS ? 0u : (row0 + g.b[q]);
       u64* v = &x[q * R];
       if (!INV) {
+        // all twiddle pairs of the round are requested before the first butterfly: in the rows pass they come from
+        // L2 (each tile has its own 63 KB of them) and ptxas otherwise leaves half of the loads in mid-round
+        ulonglong2 tw[R - 1];
 #pragma unroll
         for (int u = 0; u < NS; u++) {
-          const int half = R >> (u + 1), tl = t + u, s = s_base + tl;
+          const int tl = t + u, s = s_base + tl;
           const ulonglong2* tp = L.om + ((1u << s) + (root0 << tl) + (g.a_hi[q] << u));
 #pragma unroll
+          for (int m = 0; m < (1 << u); m++) tw[(1 << u) - 1 + m] = __ldg(tp + m);
+        }
+#pragma unroll
+        for (int u = 0; u < NS; u++) {
+          const int half = R >> (u + 1);
+#pragma unroll
           for (int m = 0; m < (1 << u); m++) {
-            const ulonglong2 w = __ldg(tp + m);
+            const ulonglong2 w = tw[(1 << u) - 1 + m];
 #pragma unroll
             for (int e = 0; e < half; e++) {
               const int jj = m * 2 * half + e;
@@ -109,6 +118,7 @@ struct FastTile {
               v[e + half] = csub(mul_const_lazy<SOL>(p2 + a - b2, L.zn, L.zn_s, p, c), p);
             }
           } else {
+            // (prefetching the round's twiddles as in the forward branch measured 6% slower here)
             const ulonglong2* tp = L.zi + ((1u << logn) - (2u << s) + (root0 << tl) + (g.a_hi[q] << u));
 #pragma unroll
             for (int m = 0; m < (1 << u); m++) {
