@@ -185,10 +185,23 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   const u64* src = A.in + (((size_t)poly * nf) << A.logn) + c0;
   const u32 cc = threadIdx.x;
 
-  for (u32 i = 0; i < nf; i++) s_r[i * TC + cc] = src[((size_t)i << A.logn) + cc];
-  for (u32 jj = 0; jj < n_out4; jj++)
-    for (u32 ii = cc; ii < nf; ii += TC)
-      s_omega[ii * n_out4 + jj] = jj < n_out ? S.omega[(size_t)(A.start + jj) * nf + ii] : 0;
+  // Every thread fetches its own column of the source residues with asynchronous 8-byte copies (all n_from
+  // requests in flight at once, no registers held, and no CTA barrier is needed for them: a thread only ever reads
+  // back what it copied itself).  ncu r1: the former load-then-store loop left 30% of the warp samples waiting at
+  // the barrier behind eight dependent HBM round trips.
+  {
+    const u32 dst0 = (u32)__cvta_generic_to_shared(s_r + cc);
+    for (u32 i = 0; i < nf; i++)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst0 + i * TC * 8u),
+                   "l"(src + ((size_t)i << A.logn) + cc)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // the (L2-resident) tables, spread over the whole CTA
+  for (u32 idx = cc; idx < nf * n_out4; idx += TC) {
+    const u32 ii = idx / n_out4, jj = idx - ii * n_out4;
+    s_omega[idx] = jj < n_out ? S.omega[(size_t)(A.start + jj) * nf + ii] : 0;
+  }
   for (u32 i = cc; i < n_out4; i += TC) s_gamma[i] = i < n_out ? S.gamma[A.start + i] : 0;
   for (u32 i = cc; i < nf; i += TC) {
     s_tgl[i] = S.tgar_lo[i];
@@ -197,14 +210,18 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
     s_toh[i] = S.to_hi[i];
     s_tos[i] = S.to_sign[i];
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   // v = round(sum_i r_i * theta_garner_i / 2^shift)   (:260-272)
   u128 v;
   {
-    u32 acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    AccTheta at;
+    at.clear();
 #pragma unroll 2
-    for (u32 i = 0; i < nf; i++) mac_theta(acc, s_r[i * TC + cc], s_tgl[i], s_tgh[i]);
+    for (u32 i = 0; i < nf; i++) at.mac(s_r[i * TC + cc], s_tgl[i], s_tgh[i]);
+    u32 acc[7];
+    at.words(acc);
     U256 sg = u256_from_acc(acc);
     // theta_garner_shift is in [123,127] for moduli < 2^62 and <= 64 limbs (:130-142): shift-1 = 64 + bs, 58 <= bs <= 62
     const u32 bs = S.shift - 1 - 64;
@@ -217,13 +234,21 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   bool w_sign = false;
   u128 w = 0;
   if (!S.is_one) {
-    u32 pos[7] = {0, 0, 0, 0, 0, 0, 0}, neg[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (u32 i = 0; i < nf; i++) {
-      const u64 r = s_r[i * TC + cc];
-      if (s_tos[i]) mac_theta(neg, r, s_tol[i], s_toh[i]);   // table-driven, warp-uniform branch
-      else mac_theta(pos, r, s_tol[i], s_toh[i]);
+    // one pass per sign (table-driven, CTA-uniform branch) keeps a single accumulator set live
+    U256 s_pos = {0, 0, 0, 0}, s_neg = {0, 0, 0, 0};
+#pragma unroll 1
+    for (u32 sg = 0; sg < 2; sg++) {
+      AccTheta at;
+      at.clear();
+#pragma unroll 2
+      for (u32 i = 0; i < nf; i++)
+        if ((u32)s_tos[i] == sg) at.mac(s_r[i * TC + cc], s_tol[i], s_toh[i]);
+      u32 wds[7];
+      at.words(wds);
+      if (sg == 0) s_pos = u256_from_acc(wds);
+      else s_neg = u256_from_acc(wds);
     }
-    U256 so = u256_sub(u256_from_acc(pos), u256_from_acc(neg));
+    U256 so = u256_sub(s_pos, s_neg);
     U256 vt = u256_mul_128(v, S.tg_lo, S.tg_hi);
     so = S.tg_sign ? u256_add(so, vt) : u256_sub(so, vt);
     w_sign = (so.w3 != 0) || (so.w2 >> 63);
@@ -369,20 +394,31 @@ __global__ void ksmac_kernel(KsMacArgs A) {
   const u64* k0_ptr = A.k0 + ((size_t)j << A.logn) + c;
   const u64* k1_ptr = A.k1 + ((size_t)j << A.logn) + c;
   const size_t dstride = (size_t)A.Lk << A.logn;
+  // two digits per trip, the six words of the next trip requested before the multiplies of this one (the kernel
+  // is bound by HBM latency, not by the multiplier: 2 x n_dig x 8 IMAD.WIDE per 48 bytes read)
   u32 i = 0;
-  for (; i + 2 <= A.n_dig; i += 2) {   // two digits per trip: six independent loads in flight
-    const u64 t0 = t_ptr[(size_t)i * dstride], t1 = t_ptr[(size_t)(i + 1) * dstride];
-    const u64 x0 = __ldg(k0_ptr + (size_t)i * dstride), x1 = __ldg(k0_ptr + (size_t)(i + 1) * dstride);
-    const u64 y0 = __ldg(k1_ptr + (size_t)i * dstride), y1 = __ldg(k1_ptr + (size_t)(i + 1) * dstride);
-    a0.mac(t0, x0);
-    a1.mac(t0, y0);
-    a0.mac(t1, x1);
-    a1.mac(t1, y1);
+  u64 t0 = 0, t1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  if (A.n_dig >= 2) {
+    t0 = t_ptr[0], t1 = t_ptr[dstride];
+    x0 = __ldg(k0_ptr), x1 = __ldg(k0_ptr + dstride);
+    y0 = __ldg(k1_ptr), y1 = __ldg(k1_ptr + dstride);
+  }
+  for (; i + 2 <= A.n_dig; i += 2) {
+    const u64 ct0 = t0, ct1 = t1, cx0 = x0, cx1 = x1, cy0 = y0, cy1 = y1;
+    if (i + 4 <= A.n_dig) {
+      t0 = t_ptr[(size_t)(i + 2) * dstride], t1 = t_ptr[(size_t)(i + 3) * dstride];
+      x0 = __ldg(k0_ptr + (size_t)(i + 2) * dstride), x1 = __ldg(k0_ptr + (size_t)(i + 3) * dstride);
+      y0 = __ldg(k1_ptr + (size_t)(i + 2) * dstride), y1 = __ldg(k1_ptr + (size_t)(i + 3) * dstride);
+    }
+    a0.mac(ct0, cx0);
+    a1.mac(ct0, cy0);
+    a0.mac(ct1, cx1);
+    a1.mac(ct1, cy1);
   }
   if (i < A.n_dig) {
-    const u64 t0 = t_ptr[(size_t)i * dstride];
-    a0.mac(t0, __ldg(k0_ptr + (size_t)i * dstride));
-    a1.mac(t0, __ldg(k1_ptr + (size_t)i * dstride));
+    const u64 tl = t_ptr[(size_t)i * dstride];
+    a0.mac(tl, __ldg(k0_ptr + (size_t)i * dstride));
+    a1.mac(tl, __ldg(k1_ptr + (size_t)i * dstride));
   }
   const size_t o = (((size_t)ct * A.out_ct_rows + j) << A.logn) + c;
   if (A.base0) a0.add64(A.base0[o]);

@@ -261,30 +261,68 @@ __device__ __forceinline__ u64 fold192_solinas(u64 lo, u64 mid, u64 hi, u32 c) {
   return fold94_solinas(lo, mid, c);
 }
 
-// 192-bit lazy accumulator for sums of products of operands < 2^62 (used by the RNS scaler and the
-// key-switch inner product; replaces the reference's per-term Shoup reduction,
-// rns/scaler.rs:340-347 and rq/ops.rs:208, with one reduction at the end).
+// Lazy multiply-accumulate register: sum of 64x64-bit products, exact up to 2^160, reduced once at the end
+// (used by the RNS scaler and the key-switch inner product; replaces the reference's per-term Shoup
+// reduction, rns/scaler.rs:340-347 and rq/ops.rs:208).
+// The four 32x32 partial products of a term go to two column sets that are never added to each other inside the
+// loop: the even one (e0..e4, products aligned at words 0 and 2) and the odd one (o1..o3, aligned at word 1).
+// Each mad.lo.cc/madc.hi.cc pair is ONE IMAD.WIDE.U32 with carry-out (and carry-in for the second of a chain), so
+// a term costs 4 IMAD.WIDE + 2 IADD3.X -- the FMA-pipe minimum -- instead of 4 IMAD.WIDE + 9 carry-chain adds of
+// the 128-bit-product-then-192-bit-add form (ncu r1: the ALU pipe, not the multiplier, bounded that form).
 struct Acc192 {
-  u64 lo, mid, hi;
-  __device__ __forceinline__ void clear() { lo = mid = hi = 0; }
-  __device__ __forceinline__ void mac(u64 a, u64 b) {  // a, b < 2^62
-    u64 pl, ph;
-    mul128_62(a, b, pl, ph);
-    asm("add.cc.u64 %0, %0, %3;\n\t"
-        "addc.cc.u64 %1, %1, %4;\n\t"
-        "addc.u64 %2, %2, 0;"
-        : "+l"(lo), "+l"(mid), "+l"(hi)
-        : "l"(pl), "l"(ph));
+  u32 e0, e1, e2, e3, e4, o1, o2, o3;
+  __device__ __forceinline__ void clear() { e0 = e1 = e2 = e3 = e4 = o1 = o2 = o3 = 0; }
+  __device__ __forceinline__ void mac(u64 a, u64 b) {
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1;\n\t"
+        "mov.b64 {a0, a1}, %8;\n\t"
+        "mov.b64 {b0, b1}, %9;\n\t"
+        "mad.lo.cc.u32 %0, a0, b0, %0;\n\t"
+        "madc.hi.cc.u32 %1, a0, b0, %1;\n\t"
+        "madc.lo.cc.u32 %2, a1, b1, %2;\n\t"
+        "madc.hi.cc.u32 %3, a1, b1, %3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %5, a0, b1, %5;\n\t"
+        "madc.hi.cc.u32 %6, a0, b1, %6;\n\t"
+        "addc.u32 %7, %7, 0;\n\t"
+        "mad.lo.cc.u32 %5, a1, b0, %5;\n\t"
+        "madc.hi.cc.u32 %6, a1, b0, %6;\n\t"
+        "addc.u32 %7, %7, 0;\n\t"
+        "}"
+        : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(o1), "+r"(o2), "+r"(o3)
+        : "l"(a), "l"(b));
   }
   __device__ __forceinline__ void add64(u64 v) {
-    asm("add.cc.u64 %0, %0, %3;\n\t"
-        "addc.cc.u64 %1, %1, 0;\n\t"
-        "addc.u64 %2, %2, 0;"
-        : "+l"(lo), "+l"(mid), "+l"(hi)
+    asm("{\n\t"
+        ".reg .u32 v0, v1;\n\t"
+        "mov.b64 {v0, v1}, %5;\n\t"
+        "add.cc.u32 %0, %0, v0;\n\t"
+        "addc.cc.u32 %1, %1, v1;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "}"
+        : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4)
         : "l"(v));
   }
-  // canonical residue of the accumulated value; hi must be < 2^32
+  // value = hi * 2^128 + mid * 2^64 + lo
+  __device__ __forceinline__ void merged(u64& lo, u64& mid, u32& hi) const {
+    u32 w1, w2, w3;
+    asm("add.cc.u32 %0, %4, %8;\n\t"
+        "addc.cc.u32 %1, %5, %9;\n\t"
+        "addc.cc.u32 %2, %6, %10;\n\t"
+        "addc.u32 %3, %7, 0;"
+        : "=r"(w1), "=r"(w2), "=r"(w3), "=r"(hi)
+        : "r"(e1), "r"(e2), "r"(e3), "r"(e4), "r"(o1), "r"(o2), "r"(o3));
+    lo = ((u64)w1 << 32) | e0;
+    mid = ((u64)w3 << 32) | w2;
+  }
+  // canonical residue of the accumulated value (which must be < 2^160)
   __device__ __forceinline__ u64 reduce(const LimbDev& m) const {
+    u64 lo, mid;
+    u32 hi32;
+    merged(lo, mid, hi32);
+    const u64 hi = hi32;
     if (m.sol_c) return csub(fold192_solinas(lo, mid, hi, (u32)m.sol_c), m.p);
     u64 r1 = barrett128_lazy(lo, mid, m.p, m.bhi, m.blo);  // [0,2p)
     u64 hl = hi * m.c128, hh = __umul64hi(hi, m.c128);
@@ -356,6 +394,65 @@ __device__ __forceinline__ void mac_theta(u32 (&a)[7], u64 r, u64 tlo, u64 thi) 
       : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6])
       : "l"(r), "l"(tlo), "l"(thi));
 }
+
+// The same sum as repeated mac_theta calls, restructured like Acc192: r0*theta and r1*theta each go to an even
+// and an odd column set (words 0/2 and 1/3 of the product), four independent carry chains of two IMAD.WIDE and
+// one IADD3.X each, no dependence between the eight multiplies of a term.  value = A + (B + C) * 2^32 + D * 2^64.
+struct AccTheta {
+  u32 a[5], b[5], c[5], d[5];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 5; i++) a[i] = b[i] = c[i] = d[i] = 0;
+  }
+  __device__ __forceinline__ void mac(u64 r, u64 tlo, u64 thi) {
+    asm("{\n\t"
+        ".reg .u32 r0, r1, t0, t1, t2, t3;\n\t"
+        "mov.b64 {r0, r1}, %20;\n\t"
+        "mov.b64 {t0, t1}, %21;\n\t"
+        "mov.b64 {t2, t3}, %22;\n\t"
+        "mad.lo.cc.u32 %0, r0, t0, %0;\n\t"
+        "madc.hi.cc.u32 %1, r0, t0, %1;\n\t"
+        "madc.lo.cc.u32 %2, r0, t2, %2;\n\t"
+        "madc.hi.cc.u32 %3, r0, t2, %3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %5, r0, t1, %5;\n\t"
+        "madc.hi.cc.u32 %6, r0, t1, %6;\n\t"
+        "madc.lo.cc.u32 %7, r0, t3, %7;\n\t"
+        "madc.hi.cc.u32 %8, r0, t3, %8;\n\t"
+        "addc.u32 %9, %9, 0;\n\t"
+        "mad.lo.cc.u32 %10, r1, t0, %10;\n\t"
+        "madc.hi.cc.u32 %11, r1, t0, %11;\n\t"
+        "madc.lo.cc.u32 %12, r1, t2, %12;\n\t"
+        "madc.hi.cc.u32 %13, r1, t2, %13;\n\t"
+        "addc.u32 %14, %14, 0;\n\t"
+        "mad.lo.cc.u32 %15, r1, t1, %15;\n\t"
+        "madc.hi.cc.u32 %16, r1, t1, %16;\n\t"
+        "madc.lo.cc.u32 %17, r1, t3, %17;\n\t"
+        "madc.hi.cc.u32 %18, r1, t3, %18;\n\t"
+        "addc.u32 %19, %19, 0;\n\t"
+        "}"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]),
+          "+r"(b[4]), "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(d[0]), "+r"(d[1]), "+r"(d[2]),
+          "+r"(d[3]), "+r"(d[4])
+        : "l"(r), "l"(tlo), "l"(thi));
+  }
+  // the 7 little-endian words of the sum (which must be < 2^224)
+  __device__ __forceinline__ void words(u32 (&w)[7]) const {
+    u64 t = (u64)a[1] + b[0] + c[0];
+    w[0] = a[0];
+    w[1] = (u32)t;
+    t = (t >> 32) + a[2] + b[1] + c[1] + d[0];
+    w[2] = (u32)t;
+    t = (t >> 32) + a[3] + b[2] + c[2] + d[1];
+    w[3] = (u32)t;
+    t = (t >> 32) + a[4] + b[3] + c[3] + d[2];
+    w[4] = (u32)t;
+    t = (t >> 32) + b[4] + c[4] + d[3];
+    w[5] = (u32)t;
+    t = (t >> 32) + d[4];
+    w[6] = (u32)t;
+  }
+};
 
 // canonical a*b mod p for canonical a, b (Modulus::mul / mul_opt, zq/mod.rs:131-156)
 __device__ __forceinline__ u64 mulmod_limb(u64 a, u64 b, const LimbDev& m) {
