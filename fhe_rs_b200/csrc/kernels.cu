@@ -163,6 +163,24 @@ __device__ __forceinline__ U256 u256_mul_128(u128 v, u64 tlo, u64 thi) {
 // chain lacks -- ncu: the register-resident one-limb-at-a-time form ran at 0.3 IPC).
 constexpr int kScaleTC = 128;
 
+// sum_i r_i * omega_{j0+k, i} for the G (<= 4) output limbs of one group
+template <int G>
+__device__ __forceinline__ void scale_mac_group(Acc192 (&acc)[4], const u64* r_col, const ulonglong2* om, u32 nf,
+                                                u32 om_stride) {
+#pragma unroll 2
+  for (u32 i = 0; i < nf; i++) {
+    const u64 r = r_col[i * kScaleTC];
+    const ulonglong2 o0 = om[(size_t)i * om_stride];
+    acc[0].mac(r, o0.x);
+    if (G > 1) acc[1].mac(r, o0.y);
+    if (G > 2) {
+      const ulonglong2 o1 = om[(size_t)i * om_stride + 1];
+      acc[2].mac(r, o1.x);
+      if (G > 3) acc[3].mac(r, o1.y);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   extern __shared__ __align__(16) u64 smem[];
   const ScalerDev& S = A.S;
@@ -268,14 +286,13 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
 #pragma unroll
     for (int k = 0; k < 4; k++) acc[k].clear();
     const ulonglong2* om = reinterpret_cast<const ulonglong2*>(s_omega + j0);
-#pragma unroll 2
-    for (u32 i = 0; i < nf; i++) {
-      const u64 r = s_r[i * TC + cc];
-      const ulonglong2 o0 = om[(size_t)i * (n_out4 / 2)], o1 = om[(size_t)i * (n_out4 / 2) + 1];
-      acc[0].mac(r, o0.x);
-      acc[1].mac(r, o0.y);
-      acc[2].mac(r, o1.x);
-      acc[3].mac(r, o1.y);
+    // the multiplier pipe bounds this loop (bench_micro/mac_bench.cu), so the last group only multiplies for the
+    // limbs it really has (14 outputs = 4+4+4+2, not 16)
+    switch (min(4u, n_out - j0)) {
+      case 4: scale_mac_group<4>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+      case 3: scale_mac_group<3>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+      case 2: scale_mac_group<2>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+      default: scale_mac_group<1>(acc, s_r + cc, om, nf, n_out4 / 2); break;
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {

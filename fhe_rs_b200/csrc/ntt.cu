@@ -108,7 +108,9 @@ void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const Li
   second.in = out;
   second.in_div = 1;
   second.reduce_on_load = 0;
-  static const bool generic = getenv("FHE_B200_GENERIC_NTT") != nullptr;
+  // the register-resident kernels carry the Shoup butterflies only (the Solinas form measured no faster and doubled
+  // their code size); FHE_B200_SOLINAS_NTT therefore selects the generic tile kernels, which keep both
+  static const bool generic = getenv("FHE_B200_GENERIC_NTT") != nullptr || getenv("FHE_B200_SOLINAS_NTT") != nullptr;
   if (generic) {
     if (!inverse) {
       run_cols_for<false>(a, st);

@@ -280,10 +280,7 @@ __global__ void __launch_bounds__(512, 2) ntt_fast_kernel(NttArgs A) {
   }
   const LimbDev& L = A.limbs[A.ids[row % A.limbs_per_poly]];
   const bool first_pass = COLS || A.logn1 == 0;
-  if (L.sol_ntt)
-    FastTile<LOGP, COLS, INV, true>::run(src, dst, gstride_a, sm, A.reduce_on_load != 0, L, s_base, A.logn, row0, first_pass);
-  else
-    FastTile<LOGP, COLS, INV, false>::run(src, dst, gstride_a, sm, A.reduce_on_load != 0, L, s_base, A.logn, row0, first_pass);
+  FastTile<LOGP, COLS, INV, false>::run(src, dst, gstride_a, sm, A.reduce_on_load != 0, L, s_base, A.logn, row0, first_pass);
 }
 
 }  // namespace fhe_b200

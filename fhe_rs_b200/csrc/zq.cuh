@@ -35,8 +35,30 @@ __device__ __forceinline__ u64 csub(u64 x, u64 p) { return x >= p ? x - p : x; }
 
 // lazy Shoup product: a*w mod p in [0,2p) for any 64-bit a (zq/mod.rs:224-234)
 __device__ __forceinline__ u64 mul_shoup_lazy(u64 a, u64 w, u64 ws, u64 p) {
-  u64 q = __umul64hi(a, ws);
-  return a * w - q * p;
+  const u64 q = __umul64hi(a, ws);
+  // a*w - q*p (mod 2^64) as a*w + q*(-p): one accumulating chain of two IMAD.WIDE and four IMAD, no separate
+  // negation/subtraction (four ALU-pipe instructions fewer per butterfly than the two-product form)
+  const u64 np = 0 - p;
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 a0, a1, w0, w1, q0, q1, n0, n1, lo, hi;\n\t"
+      ".reg .u64 W;\n\t"
+      "mov.b64 {a0, a1}, %1;\n\t"
+      "mov.b64 {w0, w1}, %2;\n\t"
+      "mov.b64 {q0, q1}, %3;\n\t"
+      "mov.b64 {n0, n1}, %4;\n\t"
+      "mul.wide.u32 W, q0, n0;\n\t"
+      "mad.wide.u32 W, a0, w0, W;\n\t"
+      "mov.b64 {lo, hi}, W;\n\t"
+      "mad.lo.u32 hi, q0, n1, hi;\n\t"
+      "mad.lo.u32 hi, q1, n0, hi;\n\t"
+      "mad.lo.u32 hi, a0, w1, hi;\n\t"
+      "mad.lo.u32 hi, a1, w0, hi;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t"
+      "}"
+      : "=l"(r)
+      : "l"(a), "l"(w), "l"(q), "l"(np));
+  return r;
 }
 __device__ __forceinline__ u64 mul_shoup(u64 a, u64 w, u64 ws, u64 p) {
   return csub(mul_shoup_lazy(a, w, ws, p), p);
