@@ -54,6 +54,10 @@ SYMBOLS = {
     "fhe_b200_mul": (_i, [_vp, _vp, _vp, _vp]),
     "fhe_b200_relinearize": (_i, [_vp, _vp, _vp, _vp]),
     "fhe_b200_mul_relin": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "fhe_b200_multiplicator_create": (_i, [_vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _vp,
+                                           _vp, _u32, _vp, _u32, _vp]),
+    "fhe_b200_multiplicator_free": (_i, [_vp]),
+    "fhe_b200_multiplicator_multiply": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "fhe_b200_galois": (_i, [_vp, _u32, _vp, _vp, _vp]),
     "fhe_b200_substitute": (_i, [_vp, _u32, _vp, _vp]),
     "fhe_b200_switch_down": (_i, [_vp, _vp]),

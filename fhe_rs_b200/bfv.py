@@ -20,7 +20,7 @@ from . import _capi
 from ._capi import NTT, POWER_BASIS, FheError, check
 
 __all__ = ["BfvParameters", "BfvParametersBuilder", "Ciphertext", "KeySwitchingKey", "RelinearizationKey", "RGSWCiphertext",
-           "GaloisKey", "EvaluationKey", "Multiplicator", "FheError", "NTT", "POWER_BASIS"]
+           "GaloisKey", "EvaluationKey", "Multiplicator", "ScalingFactor", "FheError", "NTT", "POWER_BASIS"]
 
 
 def _ptr(a: np.ndarray) -> int:
@@ -507,19 +507,83 @@ class EvaluationKey:
         return self.gk[e].relinearize(ct)
 
 
-class Multiplicator:
-    """fhe::bfv::Multiplicator (bfv/ops/mul.rs:22-33) with the default strategy
-    (Multiplicator::default, mul.rs:101-138: extend by factor 1, scale by t/Q, relinearize)."""
+class ScalingFactor:
+    """fhe_math::rns::ScalingFactor (rns/scaler.rs:20-58): numerator / denominator."""
 
-    def __init__(self, rk: RelinearizationKey):
+    def __init__(self, numerator: int, denominator: int):
+        if denominator == 0:
+            raise FheError(_capi.INVALID_ARGUMENT, "The denominator of a scaling factor should be non-zero")
+        self.numerator, self.denominator = int(numerator), int(denominator)
+
+    @staticmethod
+    def one() -> "ScalingFactor":
+        return ScalingFactor(1, 1)
+
+    @property
+    def is_one(self) -> bool:
+        return self.numerator == self.denominator
+
+
+def _le(x: int):
+    b = int(x).to_bytes(max(1, (int(x).bit_length() + 7) // 8), "little")
+    return (C.c_uint8 * len(b)).from_buffer_copy(b), len(b)
+
+
+class Multiplicator:
+    """fhe::bfv::Multiplicator (bfv/ops/mul.rs:22-33).  `default(rk)` is the default strategy (mul.rs:101-138: extend
+    by factor 1, scale by t/Q, relinearize) on the fused path; `new` / `new_leveled` (mul.rs:37-75) build a custom
+    strategy from scaling factors and an extended basis."""
+
+    def __init__(self, rk: Optional[RelinearizationKey] = None, par: Optional[BfvParameters] = None, level: int = 0):
         self.rk = rk
-        self.par = rk.ksk.par
-        self.level = rk.ksk.ciphertext_level
+        self.par = rk.ksk.par if rk is not None else par
+        self.level = rk.ksk.ciphertext_level if rk is not None else level
         self.mod_switch = False
+        self._h = None   # custom-strategy handle
 
     @staticmethod
     def default(rk: RelinearizationKey) -> "Multiplicator":
         return Multiplicator(rk)
+
+    @staticmethod
+    def new(lhs: ScalingFactor, rhs: ScalingFactor, extended_basis, post: ScalingFactor,
+            par: BfvParameters, psi=None) -> "Multiplicator":
+        return Multiplicator.new_leveled(lhs, rhs, extended_basis, post, 0, par, psi)
+
+    @staticmethod
+    def new_leveled(lhs: ScalingFactor, rhs: ScalingFactor, extended_basis, post: ScalingFactor, level: int,
+                    par: BfvParameters, psi=None) -> "Multiplicator":
+        m = Multiplicator(None, par, level)
+        basis = np.ascontiguousarray(np.array([int(q) for q in extended_basis], dtype=np.uint64))
+        ps = None
+        if psi is not None:
+            ps = np.ascontiguousarray(np.array([int(psi[int(q)]) for q in basis], dtype=np.uint64))
+        args = []
+        for f in (lhs, rhs):
+            for v in (f.numerator, f.denominator):
+                args += list(_le(v))
+        pn, pd = _le(post.numerator), _le(post.denominator)
+        h = C.c_void_p()
+        check(_capi.lib().fhe_b200_multiplicator_create(
+            par._h, level, *args, basis.ctypes.data, len(basis), ps.ctypes.data if ps is not None else None,
+            pn[0], pn[1], pd[0], pd[1], C.byref(h)))
+        m._h = h
+        m.extended_basis = [int(q) for q in basis]
+        return m
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _capi.lib().fhe_b200_multiplicator_free(h)
+            except Exception:
+                pass
+
+    def enable_relinearization(self, rk: RelinearizationKey):  # mul.rs:141-151
+        if rk.ksk.par is not self.par or rk.ksk.ciphertext_level != self.level:
+            raise FheError(_capi.CONTEXT_MISMATCH, "ParameterMismatch")
+        self.rk = rk
+        return self
 
     def enable_mod_switching(self):  # mul.rs:155-162
         if self.level >= self.par.max_level():
@@ -531,7 +595,12 @@ class Multiplicator:
         """Multiplicator::multiply (mul.rs:165-243)."""
         if lhs.level != self.level or rhs.level != self.level:
             raise FheError(_capi.INVALID_LEVEL, "InvalidLevel")  # mul.rs:168-181
-        out = lhs._like(parts=2, level=self.level + (1 if self.mod_switch else 0))
-        check(_capi.lib().fhe_b200_mul_relin(lhs._h, rhs._h, self.rk.ksk._h, 1 if self.mod_switch else 0,
-                                             out._h, lhs.stream))
+        ms = 1 if self.mod_switch else 0
+        if self._h is None:
+            out = lhs._like(parts=2, level=self.level + ms)
+            check(_capi.lib().fhe_b200_mul_relin(lhs._h, rhs._h, self.rk.ksk._h, ms, out._h, lhs.stream))
+            return out
+        out = lhs._like(parts=2 if self.rk is not None else 3, level=self.level + ms)
+        check(_capi.lib().fhe_b200_multiplicator_multiply(
+            self._h, lhs._h, rhs._h, self.rk.ksk._h if self.rk is not None else None, ms, out._h, lhs.stream))
         return out

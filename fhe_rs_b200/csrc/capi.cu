@@ -171,6 +171,47 @@ struct fhe_b200_ksk {
   u64 *k0, *k1;
 };
 
+// Multiplicator::new / new_leveled (bfv/ops/mul.rs:37-98): custom scaling factors and extended basis.
+struct fhe_b200_multiplicator {
+  const fhe_b200_params* par;
+  u32 level = 0, L = 0, K = 0;
+  u32 nc_l = 0, nc_r = 0, nc_d = 0;     // Scaler::number_common_moduli of the two extenders and the down scaler
+  std::vector<u64> mul_moduli, plan_primes;
+  RowIds mul_ids;
+  std::vector<LimbDev> h_limbs;          // the parameter set's limbs followed by the primes only this basis has
+  LimbDev* d_limbs = nullptr;
+  ScalerData ext_l, ext_r, down;
+  std::vector<void*> d_allocs;
+  template <typename T>
+  T* to_dev(const std::vector<T>& v) {
+    if (v.empty()) return nullptr;
+    T* d = nullptr;
+    FHE_CUDA(cudaMalloc(&d, v.size() * sizeof(T)));
+    d_allocs.push_back(d);
+    FHE_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+  }
+  int prime_index(u64 q) const {
+    for (size_t i = 0; i < plan_primes.size(); i++)
+      if (plan_primes[i] == q) return (int)i;
+    return -1;
+  }
+  void upload_scaler(ScalerData& sd, const std::vector<u64>& to_moduli) {
+    ScalerDev& d = sd.dev;
+    std::memset(&d, 0, sizeof(d));
+    d.n_from = sd.h.n_from; d.n_to = sd.h.n_to; d.is_one = sd.h.is_one; d.shift = sd.h.shift;
+    d.tg_lo = sd.h.theta_gamma_lo; d.tg_hi = sd.h.theta_gamma_hi; d.tg_sign = sd.h.theta_gamma_sign;
+    for (size_t j = 0; j < to_moduli.size(); j++) d.to_ids[j] = (unsigned short)prime_index(to_moduli[j]);
+    d.gamma = to_dev(sd.h.gamma);
+    d.omega = to_dev(sd.h.omega);
+    d.to_lo = to_dev(sd.h.theta_omega_lo);
+    d.to_hi = to_dev(sd.h.theta_omega_hi);
+    d.to_sign = to_dev(sd.h.theta_omega_sign);
+    d.tgar_lo = to_dev(sd.h.theta_garner_lo);
+    d.tgar_hi = to_dev(sd.h.theta_garner_hi);
+  }
+};
+
 namespace {
 
 void params_release(const fhe_b200_params* cp) {
@@ -186,6 +227,37 @@ void params_release(const fhe_b200_params* cp) {
 const fhe_b200_params* params_retain(const fhe_b200_params* p) {
   const_cast<fhe_b200_params*>(p)->refs.fetch_add(1);
   return p;
+}
+
+// Per-prime device constants and twiddle tables (NttOperator::new, ntt/native.rs:35-73, as (value, companion) pairs).
+template <typename ToDev>
+LimbDev make_limb_dev(u64 q, const NttTablesH& t, ToDev&& to_dev) {
+  ModulusH m(q);
+  LimbDev d;
+  std::memset(&d, 0, sizeof(d));
+  d.p = q; d.p2 = 2 * q; d.bhi = m.bhi; d.blo = m.blo; d.c128 = m.c128;
+  d.ninv = t.ninv; d.zn = t.zn;
+  // limb mode: p = 2^62 - c with c < 2^28 takes the Solinas constant-multiplication form
+  const u64 cc = (1ull << 62) - q;
+  const bool sol = (q >> 61) == 1 && cc < (1ull << 28) && !getenv("FHE_B200_NO_SOLINAS");
+  // NTT butterflies: Shoup pairs by default (bench_micro/bf_bench: 3.21 vs <= 3.02 butterflies/clk/SM for every
+  // Solinas instruction selection tried); FHE_B200_SOLINAS_NTT=1 selects the (w, w*2^32 mod p) pairs instead
+  const bool sol_ntt = getenv("FHE_B200_SOLINAS_NTT") != nullptr;
+  auto pairs = [&](const std::vector<u64>& v, const std::vector<u64>& shoup) {
+    std::vector<ulonglong2> o(v.size());
+    for (size_t k = 0; k < v.size(); k++) {
+      o[k].x = v[k];
+      o[k].y = (sol && sol_ntt) ? (u64)((((u128)v[k]) << 32) % q) : shoup[k];
+    }
+    return o;
+  };
+  d.sol_c = sol ? cc : 0;
+  d.sol_ntt = (sol && sol_ntt) ? 1 : 0;
+  d.ninv_s = (sol && sol_ntt) ? (u64)((((u128)t.ninv) << 32) % q) : t.ninv_s;
+  d.zn_s = (sol && sol_ntt) ? (u64)((((u128)t.zn) << 32) % q) : t.zn_s;
+  d.om = to_dev(pairs(t.om, t.om_s));
+  d.zi = to_dev(pairs(t.zi, t.zi_s));
+  return d;
 }
 
 struct DeviceGuard {
@@ -318,10 +390,45 @@ void mul_core(const fhe_b200_params* par, const LevelData& lv, const u64* a, con
   launch_ntt(X_l, X_l, cts * 2 * E, ext_ids, par->d_limbs, logn, false, 1, false, st);
   launch_ntt(X_r, X_r, cts * 2 * E, ext_ids, par->d_limbs, logn, false, 1, false, st);
   // mul.rs:198-201
-  launch_tensor(a, b, X_l, X_r, T, cts, L, E, lv.mul_ids, par->d_limbs, logn, st);
+  launch_tensor(a, b, X_l, X_r, T, cts, L, L, L, K, lv.mul_ids, par->d_limbs, logn, st);
   // mul.rs:204-206: scale down by t/Q (backward NTT of K rows, exact scaling K -> L)
   launch_ntt(T, T, cts * 3 * K, lv.mul_ids, par->d_limbs, logn, true, 1, false, st);
   launch_scale(lv.down.dev, par->d_limbs, T, out0, out1, cts * 3, L, 0, L, split, logn, st);
+}
+
+// The same pipeline for a custom strategy (mul.rs:192-206 with the Scalers of Multiplicator::new): every extender
+// keeps its common prefix only when its factor is one (rq/scaler.rs:35-43), so a side with a non-unit factor gets all
+// K limbs from the exact scaler.  out: [cts][3][L][N] power basis.
+void mul_core_general(const fhe_b200_multiplicator* m, const u64* a, const u64* b, u32 cts, u64* out, Workspace& ws,
+                      cudaStream_t st) {
+  const fhe_b200_params* par = m->par;
+  const LevelData& lv = par->level(m->level);
+  const u32 L = m->L, K = m->K, logn = par->logn;
+  const size_t row = (size_t)1 << logn;
+  const u64* src[2] = {a, b};
+  const ScalerData* ext[2] = {&m->ext_l, &m->ext_r};
+  const u32 nc[2] = {m->nc_l, m->nc_r};
+  u64* X[2] = {nullptr, nullptr};
+  for (int s = 0; s < 2; s++) {
+    const u32 E = K - nc[s];
+    if (!E) continue;
+    u64* pb = ws.words((size_t)cts * 2 * L * row);
+    X[s] = ws.words((size_t)cts * 2 * E * row);
+    launch_ntt(src[s], pb, cts * 2 * L, lv.ctx_ids, par->d_limbs, logn, true, 1, false, st);
+    launch_scale(ext[s]->dev, m->d_limbs, pb, X[s], nullptr, cts * 2, E, nc[s], E, 0, logn, st);
+    RowIds ids;
+    std::memset(&ids, 0, sizeof(ids));
+    ids.limbs_per_poly = E;
+    for (u32 j = 0; j < E; j++) ids.ids[j] = m->mul_ids.ids[nc[s] + j];
+    launch_ntt(X[s], X[s], cts * 2 * E, ids, m->d_limbs, logn, false, 1, false, st);
+  }
+  u64* T = ws.words((size_t)cts * 3 * K * row);
+  launch_tensor(a, b, X[0], X[1], T, cts, L, nc[0], nc[1], K, m->mul_ids, m->d_limbs, logn, st);
+  launch_ntt(T, T, cts * 3 * K, m->mul_ids, m->d_limbs, logn, true, 1, false, st);
+  if (m->nc_d)  // common prefix of a factor-one down scaler: kept as is (power basis here, transformed by the caller)
+    FHE_CUDA(cudaMemcpy2DAsync(out, L * row * 8, T, K * row * 8, m->nc_d * row * 8, (size_t)cts * 3,
+                               cudaMemcpyDeviceToDevice, st));
+  launch_scale(m->down.dev, m->d_limbs, T, out + m->nc_d * row, nullptr, cts * 3, L, m->nc_d, L - m->nc_d, 0, logn, st);
 }
 
 }  // namespace
@@ -409,33 +516,7 @@ static int params_build(int device, uint32_t degree, const std::vector<u64>& mod
     u64 r = psi ? psi[i] : default_psi(q, degree);
     p->psi.push_back(r);
     p->tables.push_back(make_ntt_tables(q, degree, r));
-    const NttTablesH& t = p->tables.back();
-    ModulusH m(q);
-    LimbDev d;
-    std::memset(&d, 0, sizeof(d));
-    d.p = q; d.p2 = 2 * q; d.bhi = m.bhi; d.blo = m.blo; d.c128 = m.c128;
-    d.ninv = t.ninv; d.zn = t.zn;
-    // limb mode: p = 2^62 - c with c < 2^28 takes the Solinas constant-multiplication form
-    const u64 cc = (1ull << 62) - q;
-    const bool sol = (q >> 61) == 1 && cc < (1ull << 28) && !getenv("FHE_B200_NO_SOLINAS");
-    // NTT butterflies: Shoup pairs by default (bench_micro/bf_bench: 3.21 vs <= 3.02 butterflies/clk/SM for every
-    // Solinas instruction selection tried); FHE_B200_SOLINAS_NTT=1 selects the (w, w*2^32 mod p) pairs instead
-    const bool sol_ntt = getenv("FHE_B200_SOLINAS_NTT") != nullptr;
-    auto pairs = [&](const std::vector<u64>& v, const std::vector<u64>& shoup) {
-      std::vector<ulonglong2> o(v.size());
-      for (size_t k = 0; k < v.size(); k++) {
-        o[k].x = v[k];
-        o[k].y = (sol && sol_ntt) ? (u64)((((u128)v[k]) << 32) % q) : shoup[k];
-      }
-      return o;
-    };
-    d.sol_c = sol ? cc : 0;
-    d.sol_ntt = (sol && sol_ntt) ? 1 : 0;
-    d.ninv_s = (sol && sol_ntt) ? (u64)((((u128)t.ninv) << 32) % q) : t.ninv_s;
-    d.zn_s = (sol && sol_ntt) ? (u64)((((u128)t.zn) << 32) % q) : t.zn_s;
-    d.om = p->to_dev(pairs(t.om, t.om_s));
-    d.zi = p->to_dev(pairs(t.zi, t.zi_s));
-    p->h_limbs.push_back(d);
+    p->h_limbs.push_back(make_limb_dev(q, p->tables.back(), [&](const std::vector<ulonglong2>& v) { return p->to_dev(v); }));
   }
   p->d_limbs = p->to_dev(p->h_limbs);
   *out = p.release();
@@ -784,6 +865,155 @@ int fhe_b200_mul_relin(const fhe_b200_batch* a, const fhe_b200_batch* b, const f
   }
   FHE_CUDA(cudaGetLastError());
   out2->repr = FHE_B200_NTT;
+  API_END
+}
+
+// ---- custom multiplication strategies
+int fhe_b200_multiplicator_create(const fhe_b200_params* p, uint32_t level, const uint8_t* lhs_num, uint32_t lhs_num_len,
+                                  const uint8_t* lhs_den, uint32_t lhs_den_len, const uint8_t* rhs_num,
+                                  uint32_t rhs_num_len, const uint8_t* rhs_den, uint32_t rhs_den_len,
+                                  const uint64_t* extended_basis, uint32_t n_basis, const uint64_t* psi,
+                                  const uint8_t* post_num, uint32_t post_num_len, const uint8_t* post_den,
+                                  uint32_t post_den_len, fhe_b200_multiplicator** out) {
+  API_BEGIN
+  REQUIRE(p && out && extended_basis && n_basis && lhs_num && lhs_den && rhs_num && rhs_den && post_num && post_den,
+          FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE(n_basis <= (u32)kMaxPos, FHE_B200_UNSUPPORTED, "too many limbs");
+  const LevelData& lv = p->level(level);   // context_at_level: InvalidLevel when out of range
+  DeviceGuard g(p);
+  std::unique_ptr<fhe_b200_multiplicator> m(new fhe_b200_multiplicator());
+  struct Cleanup {   // frees the device tables if construction throws
+    fhe_b200_multiplicator* m;
+    ~Cleanup() { if (m) { for (void* d : m->d_allocs) cudaFree(d); cudaGetLastError(); } }
+  } cleanup{m.get()};
+  m->par = p;
+  m->level = level;
+  m->L = lv.L;
+  m->K = n_basis;
+  m->mul_moduli.assign(extended_basis, extended_basis + n_basis);
+  // Context::new(extended_basis) (rq/context.rs:42-92): distinct NTT-friendly primes
+  for (u32 i = 0; i < n_basis; i++) {
+    const u64 q = extended_basis[i];
+    for (u32 j = 0; j < i; j++) REQUIRE(extended_basis[j] != q, FHE_B200_INVALID_MODULUS, "DuplicateModuli");
+    REQUIRE(q >= 2 && (q >> 62) == 0, FHE_B200_INVALID_MODULUS, "InvalidModulus: " + std::to_string(q));
+    REQUIRE(q % (2 * (u64)p->N) == 1 && is_prime_u64(q), FHE_B200_NTT_UNAVAILABLE,
+            "modulus does not support the NTT: " + std::to_string(q));
+  }
+  m->plan_primes = p->primes;
+  m->h_limbs = p->h_limbs;
+  std::memset(&m->mul_ids, 0, sizeof(RowIds));
+  m->mul_ids.limbs_per_poly = n_basis;
+  for (u32 i = 0; i < n_basis; i++) {
+    const u64 q = extended_basis[i];
+    int idx = m->prime_index(q);
+    if (idx >= 0 && psi && psi[i] != p->psi[(size_t)idx] && (size_t)idx < p->primes.size())
+      throw FheError(FHE_B200_INVALID_ARGUMENT, "psi differs from the parameter set's root for " + std::to_string(q));
+    if (idx < 0) {
+      const u64 r = psi ? psi[i] : default_psi(q, p->N);
+      NttTablesH t = make_ntt_tables(q, p->N, r);
+      idx = (int)m->plan_primes.size();
+      m->plan_primes.push_back(q);
+      m->h_limbs.push_back(make_limb_dev(q, t, [&](const std::vector<ulonglong2>& v) { return m->to_dev(v); }));
+    }
+    m->mul_ids.ids[i] = (unsigned short)idx;
+  }
+  m->d_limbs = m->to_dev(m->h_limbs);
+  std::vector<u64> base(p->moduli.begin(), p->moduli.begin() + lv.L);
+  RnsContextH from(base), to(m->mul_moduli);
+  auto factor = [](const uint8_t* b, uint32_t n) { return BigUint::from_le_bytes(b, n); };
+  const BigUint ln = factor(lhs_num, lhs_num_len), ld = factor(lhs_den, lhs_den_len);
+  const BigUint rn = factor(rhs_num, rhs_num_len), rd = factor(rhs_den, rhs_den_len);
+  const BigUint pn = factor(post_num, post_num_len), pd = factor(post_den, post_den_len);
+  REQUIRE(!ld.is_zero() && !rd.is_zero() && !pd.is_zero(), FHE_B200_INVALID_ARGUMENT, "zero denominator");
+  m->ext_l.h = make_scaler_tables(from, to, ln, ld);
+  m->ext_r.h = make_scaler_tables(from, to, rn, rd);
+  m->down.h = make_scaler_tables(to, from, pn, pd);
+  auto common = [&](const ScalerData& sd, const std::vector<u64>& x, const std::vector<u64>& y) {
+    u32 n = 0;
+    if (sd.h.is_one)
+      while (n < x.size() && n < y.size() && x[n] == y[n]) n++;
+    return n;
+  };
+  m->nc_l = common(m->ext_l, base, m->mul_moduli);
+  m->nc_r = common(m->ext_r, base, m->mul_moduli);
+  m->nc_d = common(m->down, m->mul_moduli, base);
+  m->upload_scaler(m->ext_l, m->mul_moduli);
+  m->upload_scaler(m->ext_r, m->mul_moduli);
+  m->upload_scaler(m->down, base);
+  params_retain(p);
+  cleanup.m = nullptr;
+  *out = m.release();
+  API_END
+}
+
+int fhe_b200_multiplicator_free(fhe_b200_multiplicator* m) {
+  if (!m) return FHE_B200_OK;
+  if (m->par->device >= 0) {
+    cudaSetDevice(m->par->device);
+    for (void* d : m->d_allocs) cudaFree(d);
+    cudaGetLastError();
+  }
+  params_release(m->par);
+  delete m;
+  return FHE_B200_OK;
+}
+
+int fhe_b200_multiplicator_multiply(const fhe_b200_multiplicator* m, const fhe_b200_batch* a, const fhe_b200_batch* b,
+                                    const fhe_b200_ksk* rk, int mod_switch, fhe_b200_batch* out, void* stream) {
+  API_BEGIN
+  REQUIRE(m && a && b && out, FHE_B200_INVALID_ARGUMENT, "null argument");
+  const fhe_b200_params* par = m->par;
+  REQUIRE(a->par == par && b->par == par && out->par == par, FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch");
+  REQUIRE(a->level == m->level && b->level == m->level, FHE_B200_INVALID_LEVEL, "InvalidLevel");  // mul.rs:168-181
+  REQUIRE(!a->mul_basis && !b->mul_basis && !out->mul_basis, FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
+  const u32 out_parts = rk ? 2 : 3;
+  REQUIRE(a->parts == 2 && b->parts == 2 && out->parts == out_parts, FHE_B200_BAD_POLY_COUNT,
+          "MultiplicationPolynomialCount");
+  REQUIRE(a->count == b->count && a->count == out->count, FHE_B200_INVALID_ARGUMENT, "batch sizes differ");
+  need_repr(a, FHE_B200_NTT);
+  need_repr(b, FHE_B200_NTT);
+  if (rk) {   // enable_relinearization (mul.rs:141-151): the key must live at the multiplicator's context
+    REQUIRE(rk->par == par && rk->ct_level == m->level, FHE_B200_CONTEXT_MISMATCH,
+            "ParameterMismatch: relinearization key and multiplicator contexts differ");
+  }
+  const LevelData& lv = par->level(m->level);
+  if (mod_switch) {
+    REQUIRE(lv.L >= 2, FHE_B200_NO_MORE_CONTEXT, "NoMoreContext");  // mul.rs:155-162
+    REQUIRE(out->level == m->level + 1, FHE_B200_INVALID_LEVEL, "output batch must be one level down");
+  } else {
+    REQUIRE(out->level == m->level, FHE_B200_INVALID_LEVEL, "output batch must be at the operand level");
+  }
+  DeviceGuard g(par);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row = (size_t)1 << par->logn, L = lv.L;
+  for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
+    const u32 n = std::min(chunk_size(), a->count - c0);
+    Workspace ws(st);
+    const bool direct = !rk && !mod_switch;
+    u64* W = direct ? out->d + (size_t)c0 * 3 * L * row : ws.words((size_t)n * 3 * L * row);
+    mul_core_general(m, a->d + (size_t)c0 * 2 * L * row, b->d + (size_t)c0 * 2 * L * row, n, W, ws, st);
+    u64* o = W;   // [n][out_parts][L][N]
+    if (rk) {
+      o = mod_switch ? ws.words((size_t)n * 2 * L * row) : out->d + (size_t)c0 * 2 * L * row;
+      u64* c2 = ws.words((size_t)n * L * row);
+      FHE_CUDA(cudaMemcpy2DAsync(o, 2 * L * row * 8, W, 3 * L * row * 8, 2 * L * row * 8, n, cudaMemcpyDeviceToDevice, st));
+      FHE_CUDA(cudaMemcpy2DAsync(c2, L * row * 8, W + 2 * L * row, 3 * L * row * 8, L * row * 8, n,
+                                 cudaMemcpyDeviceToDevice, st));
+      launch_ntt(o, o, n * 2 * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+      key_switch_apply(par, rk, c2, n, o, 1, nullptr, ws, st);   // mul.rs:210-228
+    } else {
+      launch_ntt(o, o, n * 3 * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+    }
+    if (mod_switch) {  // Ciphertext::switch_down, ciphertext.rs:148-161
+      launch_ntt(o, o, n * out_parts * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
+      u64* dst = out->d + (size_t)c0 * out_parts * (L - 1) * row;
+      launch_switch_down(lv.sd, o, dst, n * out_parts, (u32)L, lv.ctx_ids, par->d_limbs, par->logn, st);
+      const LevelData& nl = par->level(m->level + 1);
+      launch_ntt(dst, dst, n * out_parts * (u32)(L - 1), nl.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+    }
+  }
+  FHE_CUDA(cudaGetLastError());
+  out->repr = FHE_B200_NTT;
   API_END
 }
 

@@ -41,10 +41,10 @@ void launch_mul_plain(u64* a, const u64* pt, u32 cts, u32 parts, u32 n_pt, const
                       u32 logn, cudaStream_t st);
 
 // tensor product of two 2-part ciphertexts over the multiplication basis (mul.rs:198-201).
-// a,b: [ct][2][L][N] (common-prefix limbs, NTT); xa,xb: [ct][2][E][N] (extension limbs, NTT);
-// out: [ct][3][K][N].
-void launch_tensor(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 E,
-                   const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st);
+// a,b: [ct][2][L][N] NTT (supply the first nca / ncb mul-basis limbs of their side: the common prefix a factor-one
+// extender keeps); xa: [ct][2][K-nca][N], xb: [ct][2][K-ncb][N] (the scaled limbs, NTT); out: [ct][3][K][N].
+void launch_tensor(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 nca,
+                   u32 ncb, u32 K, const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st);
 
 // exact RNS scaler (rns/scaler.rs:249-352), tables resident on the device
 struct ScalerDev {

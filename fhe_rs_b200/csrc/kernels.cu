@@ -67,13 +67,16 @@ __global__ void mul_plain_kernel(MulPlainArgs A) {
 struct TensorArgs {
   const u64 *a, *b, *xa, *xb;
   u64* out;
-  u32 cts, L, E, logn;
+  u32 cts, L, nca, ncb, K, logn;
   const LimbDev* limbs;
   unsigned short ids[kMaxPos];
 };
-// c0 = a0*b0, c1 = a0*b1 + a1*b0, c2 = a1*b1 (bfv/ops/mul.rs:198-201; Modulus::mul_vec zq/mod.rs:332)
+// c0 = a0*b0, c1 = a0*b1 + a1*b0, c2 = a1*b1 (bfv/ops/mul.rs:198-201; Modulus::mul_vec zq/mod.rs:332).
+// Operand x (x = a, b) supplies its first nc_x mul-basis limbs from the ciphertext itself ([ct][2][L][N], the
+// common prefix a factor-one extender keeps, rq/scaler.rs:61-65) and the other K - nc_x from the scaled rows
+// ([ct][2][K - nc_x][N]).
 __global__ void tensor_kernel(TensorArgs A) {
-  const u32 N = 1u << A.logn, K = A.L + A.E;
+  const u32 N = 1u << A.logn, K = A.K;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over cts*K*N
   size_t total = (size_t)A.cts * K << A.logn;
   if (idx >= total) return;
@@ -82,14 +85,21 @@ __global__ void tensor_kernel(TensorArgs A) {
   u32 pos = row % K, ct = row / K;
   const LimbDev& M = A.limbs[A.ids[pos]];
   u64 a0, a1, b0, b1;
-  if (pos < A.L) {
+  if (pos < A.nca) {
     size_t o = (((size_t)ct * 2) * A.L + pos) << A.logn;
     a0 = A.a[o + c]; a1 = A.a[o + ((size_t)A.L << A.logn) + c];
+  } else {
+    const u32 E = K - A.nca;
+    size_t o = (((size_t)ct * 2) * E + (pos - A.nca)) << A.logn;
+    a0 = A.xa[o + c]; a1 = A.xa[o + ((size_t)E << A.logn) + c];
+  }
+  if (pos < A.ncb) {
+    size_t o = (((size_t)ct * 2) * A.L + pos) << A.logn;
     b0 = A.b[o + c]; b1 = A.b[o + ((size_t)A.L << A.logn) + c];
   } else {
-    size_t o = (((size_t)ct * 2) * A.E + (pos - A.L)) << A.logn;
-    a0 = A.xa[o + c]; a1 = A.xa[o + ((size_t)A.E << A.logn) + c];
-    b0 = A.xb[o + c]; b1 = A.xb[o + ((size_t)A.E << A.logn) + c];
+    const u32 E = K - A.ncb;
+    size_t o = (((size_t)ct * 2) * E + (pos - A.ncb)) << A.logn;
+    b0 = A.xb[o + c]; b1 = A.xb[o + ((size_t)E << A.logn) + c];
   }
   u64 c0 = mulmod_limb(a0, b0, M);
   u64 c2 = mulmod_limb(a1, b1, M);
@@ -565,14 +575,14 @@ void launch_mul_plain(u64* a, const u64* pt, u32 cts, u32 parts, u32 n_pt, const
   g_launches++;
 }
 
-void launch_tensor(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 E,
-                   const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st) {
+void launch_tensor(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 nca,
+                   u32 ncb, u32 K, const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st) {
   TensorArgs A;
   A.a = a; A.b = b; A.xa = xa; A.xb = xb; A.out = out;
-  A.cts = cts; A.L = L; A.E = E; A.logn = logn;
+  A.cts = cts; A.L = L; A.nca = nca; A.ncb = ncb; A.K = K; A.logn = logn;
   A.limbs = limbs;
   copy_ids(A.ids, mul_ids);
-  size_t total = ((size_t)cts * (L + E)) << logn;
+  size_t total = ((size_t)cts * K) << logn;
   if (!total) return;
   tensor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
   g_launches++;

@@ -63,6 +63,8 @@ typedef struct fhe_b200_params fhe_b200_params; /* == Arc<BfvParameters> (bfv/pa
 typedef struct fhe_b200_batch fhe_b200_batch;   /* == Vec<Ciphertext> of one level (bfv/ciphertext.rs:18-32),
                                                    device resident, [count][parts][limbs][N] u64               */
 typedef struct fhe_b200_ksk fhe_b200_ksk;       /* == KeySwitchingKey (bfv/keys/key_switching_key.rs:22-45)     */
+typedef struct fhe_b200_multiplicator fhe_b200_multiplicator; /* == Multiplicator with a custom strategy
+                                                   (bfv/ops/mul.rs:22-98)                                        */
 
 const char* fhe_b200_version(void);
 const char* fhe_b200_last_error(void);
@@ -142,6 +144,25 @@ int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_
  * additionally applies Ciphertext::switch_down (mul.rs:238) and out2 must be at level+1. */
 int fhe_b200_mul_relin(const fhe_b200_batch* a, const fhe_b200_batch* b, const fhe_b200_ksk* rk,
                        int mod_switch, fhe_b200_batch* out2, void* stream);
+/* Multiplicator::new / new_leveled (bfv/ops/mul.rs:37-98): custom strategy.  Each ScalingFactor (rns/scaler.rs:20-58)
+ * is a numerator / denominator pair of little-endian byte strings (BigUint::to_bytes_le).  extended_basis are the
+ * n_basis moduli of the multiplication context (Context::new(extended_basis), mul.rs:82); psi (nullable) gives the
+ * 2N-th root per basis prime (default rule of fhe_b200_params_create otherwise; primes shared with the parameter set
+ * reuse its tables).  As in rq/scaler.rs:35-43 an extender keeps the common prefix of the two bases only when its
+ * factor is one.  Errors: InvalidLevel, DuplicateModuli / InvalidModulus, NTT_UNAVAILABLE. */
+int fhe_b200_multiplicator_create(const fhe_b200_params* p, uint32_t level, const uint8_t* lhs_num, uint32_t lhs_num_len,
+                                  const uint8_t* lhs_den, uint32_t lhs_den_len, const uint8_t* rhs_num,
+                                  uint32_t rhs_num_len, const uint8_t* rhs_den, uint32_t rhs_den_len,
+                                  const uint64_t* extended_basis, uint32_t n_basis, const uint64_t* psi,
+                                  const uint8_t* post_num, uint32_t post_num_len, const uint8_t* post_den,
+                                  uint32_t post_den_len, fhe_b200_multiplicator** out);
+int fhe_b200_multiplicator_free(fhe_b200_multiplicator* m);
+/* Multiplicator::multiply (mul.rs:165-243) with that strategy.  rk == NULL: no relinearization, out has 3 parts;
+ * otherwise enable_relinearization(rk) semantics (mul.rs:141-151: the key must be for the multiplicator's level,
+ * ParameterMismatch if not) and out has 2 parts.  mod_switch != 0: enable_mod_switching (mul.rs:155-162,
+ * NoMoreContext at the last level), out must be at level+1. */
+int fhe_b200_multiplicator_multiply(const fhe_b200_multiplicator* m, const fhe_b200_batch* a, const fhe_b200_batch* b,
+                                    const fhe_b200_ksk* rk, int mod_switch, fhe_b200_batch* out, void* stream);
 /* GaloisKey::relinearize (keys/galois_key.rs:63-86) for substitution exponent `exponent`
  * (column rotation by i <-> 3^i mod 2N, row swap <-> 2N-1; evaluation_key.rs:118, :278-286) */
 int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_ksk* gk,

@@ -245,26 +245,81 @@ class EvaluationKey {
   std::map<uint32_t, std::shared_ptr<GaloisKey>> gk_;
 };
 
+// fhe_math::rns::ScalingFactor (rns/scaler.rs:20-58): numerator / denominator as little-endian byte strings
+// (BigUint::to_bytes_le)
+struct ScalingFactor {
+  std::vector<uint8_t> numerator, denominator;
+  static ScalingFactor one() { return ScalingFactor{{1}, {1}}; }
+  static ScalingFactor from_u64(uint64_t num, uint64_t den) {
+    auto le = [](uint64_t v) {
+      std::vector<uint8_t> b;
+      do { b.push_back((uint8_t)v); v >>= 8; } while (v);
+      return b;
+    };
+    return ScalingFactor{le(num), le(den)};
+  }
+};
+
 class Multiplicator {
  public:
   // Multiplicator::default (ops/mul.rs:101)
-  static Multiplicator default_(const RelinearizationKey& rk) { return Multiplicator(rk); }
+  static Multiplicator default_(const RelinearizationKey& rk) {
+    Multiplicator m(rk.ksk->par(), rk.ksk->ciphertext_level());
+    m.rk_ = std::make_shared<RelinearizationKey>(rk);
+    return m;
+  }
+  // Multiplicator::new (ops/mul.rs:37-53)
+  static Multiplicator new_(const ScalingFactor& lhs, const ScalingFactor& rhs, const std::vector<uint64_t>& extended_basis,
+                            const ScalingFactor& post, std::shared_ptr<BfvParameters> par) {
+    return new_leveled(lhs, rhs, extended_basis, post, 0, std::move(par));
+  }
+  // Multiplicator::new_leveled (ops/mul.rs:56-75)
+  static Multiplicator new_leveled(const ScalingFactor& lhs, const ScalingFactor& rhs,
+                                   const std::vector<uint64_t>& extended_basis, const ScalingFactor& post,
+                                   uint32_t level, std::shared_ptr<BfvParameters> par) {
+    Multiplicator m(par, level);
+    fhe_b200_multiplicator* h = nullptr;
+    check(fhe_b200_multiplicator_create(par->handle(), level, lhs.numerator.data(), (uint32_t)lhs.numerator.size(),
+                                        lhs.denominator.data(), (uint32_t)lhs.denominator.size(), rhs.numerator.data(),
+                                        (uint32_t)rhs.numerator.size(), rhs.denominator.data(),
+                                        (uint32_t)rhs.denominator.size(), extended_basis.data(),
+                                        (uint32_t)extended_basis.size(), nullptr, post.numerator.data(),
+                                        (uint32_t)post.numerator.size(), post.denominator.data(),
+                                        (uint32_t)post.denominator.size(), &h));
+    m.h_ = std::shared_ptr<fhe_b200_multiplicator>(h, [](fhe_b200_multiplicator* x) { fhe_b200_multiplicator_free(x); });
+    return m;
+  }
+  // Multiplicator::enable_relinearization (ops/mul.rs:141-151)
+  void enable_relinearization(const RelinearizationKey& rk) {
+    if (rk.ksk->par() != par_ || rk.ksk->ciphertext_level() != level_)
+      throw Error(FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch");
+    rk_ = std::make_shared<RelinearizationKey>(rk);
+  }
   // Multiplicator::enable_mod_switching (ops/mul.rs:155)
   void enable_mod_switching() {
-    if (level_ >= rk_.ksk->par()->max_level()) throw Error(FHE_B200_NO_MORE_CONTEXT, "NoMoreContext");
+    if (level_ >= par_->max_level()) throw Error(FHE_B200_NO_MORE_CONTEXT, "NoMoreContext");
     mod_switch_ = true;
   }
   // Multiplicator::multiply (ops/mul.rs:165)
   Ciphertext multiply(const Ciphertext& lhs, const Ciphertext& rhs) const {
     if (lhs.level() != level_ || rhs.level() != level_) throw Error(FHE_B200_INVALID_LEVEL, "InvalidLevel");
-    Ciphertext out(lhs.par(), lhs.count(), 2, level_ + (mod_switch_ ? 1 : 0), Representation::Ntt, lhs.stream());
-    check(fhe_b200_mul_relin(lhs.handle(), rhs.handle(), rk_.ksk->handle(), mod_switch_ ? 1 : 0, out.handle(), lhs.stream()));
+    const uint32_t parts = rk_ ? 2 : 3;
+    Ciphertext out(lhs.par(), lhs.count(), parts, level_ + (mod_switch_ ? 1 : 0), Representation::Ntt, lhs.stream());
+    if (!h_) {
+      check(fhe_b200_mul_relin(lhs.handle(), rhs.handle(), rk_->ksk->handle(), mod_switch_ ? 1 : 0, out.handle(),
+                               lhs.stream()));
+    } else {
+      check(fhe_b200_multiplicator_multiply(h_.get(), lhs.handle(), rhs.handle(), rk_ ? rk_->ksk->handle() : nullptr,
+                                            mod_switch_ ? 1 : 0, out.handle(), lhs.stream()));
+    }
     return out;
   }
 
  private:
-  explicit Multiplicator(const RelinearizationKey& rk) : rk_(rk), level_(rk.ksk->ciphertext_level()) {}
-  RelinearizationKey rk_;
+  Multiplicator(std::shared_ptr<BfvParameters> par, uint32_t level) : par_(std::move(par)), level_(level) {}
+  std::shared_ptr<BfvParameters> par_;
+  std::shared_ptr<RelinearizationKey> rk_;
+  std::shared_ptr<fhe_b200_multiplicator> h_;   // custom strategy; empty = fused default path
   uint32_t level_;
   bool mod_switch_ = false;
 };

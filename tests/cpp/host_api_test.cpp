@@ -47,6 +47,41 @@ int main(int argc, char** argv) {
     if (m.multiply(B, A).to_host() != P1) { printf("FAIL commutativity\n"); return 1; }
     // wire format round trip (Rq.coefficients blobs)
     if (Ciphertext::from_packed(par, A.to_packed(), count).to_host() != wa) { printf("FAIL wire round trip\n"); return 1; }
+    // custom strategy (Multiplicator::new, ops/mul.rs:37): the default strategy rebuilt from its parts must agree
+    // bit for bit with the fused default path
+    {
+      uint32_t nb = 0;
+      fhe_b200::check(fhe_b200_params_mul_basis(par->handle(), 0, nullptr, &nb));
+      std::vector<uint64_t> basis(nb);
+      fhe_b200::check(fhe_b200_params_mul_basis(par->handle(), 0, basis.data(), &nb));
+      // post factor t/Q: Q as little-endian bytes by schoolbook multiplication of the moduli
+      std::vector<uint64_t> mods(nmod);
+      fhe_b200::check(fhe_b200_params_moduli(par->handle(), mods.data()));
+      std::vector<uint8_t> Q{1};
+      for (uint64_t q : mods) {
+        std::vector<uint8_t> r(Q.size() + 8, 0);
+        for (size_t i = 0; i < Q.size(); i++) {
+          unsigned __int128 carry = 0;
+          for (size_t j = 0; j < 8; j++) {
+            unsigned __int128 cur = (unsigned __int128)r[i + j] + (unsigned __int128)Q[i] * ((q >> (8 * j)) & 0xff) + carry;
+            r[i + j] = (uint8_t)cur;
+            carry = cur >> 8;
+          }
+          for (size_t k = i + 8; carry && k < r.size(); k++) {
+            unsigned __int128 cur = (unsigned __int128)r[k] + carry;
+            r[k] = (uint8_t)cur;
+            carry = cur >> 8;
+          }
+        }
+        Q = r;
+      }
+      ScalingFactor post = ScalingFactor::from_u64(1153, 1);
+      post.denominator = Q;
+      auto mc = Multiplicator::new_(ScalingFactor::one(), ScalingFactor::one(), basis, post, par);
+      if (mc.multiply(A, B).len() != 3) { printf("FAIL custom parts\n"); return 1; }
+      mc.enable_relinearization(rk);
+      if (mc.multiply(A, B).to_host() != P1) { printf("FAIL custom strategy != default\n"); return 1; }
+    }
     // error behaviour
     try {
       m.multiply(C3, B);

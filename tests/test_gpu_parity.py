@@ -182,6 +182,99 @@ def test_mul_relin_against_oracle(oracle, F, degree, nmod, t):
 
 
 @pytest.mark.parametrize("degree,nmod", [(16, 3), (64, 2), (4096, 2)])
+def test_custom_multiplication_strategy(oracle, F, degree, nmod):
+    """Multiplicator::new / new_leveled (mul.rs:37-98) and the reference's `different_mul_strategy` test
+    (mul.rs:369-418): lhs factor one, rhs factor P/Q, post factor t/P over base + extra primes; with and without
+    relinearization and modulus switching; and the default strategy rebuilt through the custom entry point equals
+    the fused default path."""
+    t = 1153 if degree < 4096 else 1032193
+    opar, gpar, rng = make_pair(oracle, F, degree, nmod, t, 900 + degree)
+    sk, ork, grk, _, _ = _keys(oracle, F, opar, gpar, rng)
+    basis = list(opar.moduli)
+    for _ in range(nmod):
+        basis.append(oracle.generate_prime(62, 2 * degree, basis[-1]))
+    P = 1
+    for q in basis[nmod:]:
+        P *= q
+    Q = opar.context_at_level(0).modulus()
+    count = 2
+    msgs = rng.integers(0, t, size=(count, degree))
+    octa = [sk.encrypt(m, 0, rng) for m in msgs]
+    octb = [sk.encrypt(m, 0, rng) for m in msgs]
+    A = F.Ciphertext.from_host(gpar, np.stack([c.to_array() for c in octa]))
+    B = F.Ciphertext.from_host(gpar, np.stack([c.to_array() for c in octb]))
+
+    om = oracle.Multiplicator(opar, oracle.ScalingFactor.one(), oracle.ScalingFactor(P, Q), basis,
+                              oracle.ScalingFactor(t, P))
+    gm = F.Multiplicator.new(F.ScalingFactor.one(), F.ScalingFactor(P, Q), basis, F.ScalingFactor(t, P), gpar)
+    out = gm.multiply(A, B)
+    assert len(out) == 3 and out.level == 0
+    got = out.to_host()
+    for i in range(count):
+        assert (got[i] == om.multiply(octa[i], octb[i]).to_array()).all()
+    if degree <= 64:   # decrypt-correctness of the device result
+        res = oracle.Ciphertext.from_array(opar, got[0], 0)
+        exp = np.zeros(degree, dtype=object)
+        for x in range(degree):
+            for y in range(degree):
+                k, v = x + y, int(msgs[0][x]) * int(msgs[0][y])
+                if k < degree:
+                    exp[k] = (exp[k] + v) % t
+                else:
+                    exp[k - degree] = (exp[k - degree] - v) % t
+        assert (sk.decrypt(res).astype(object) == exp).all()
+    # + relinearization (enable_relinearization, mul.rs:141-151)
+    om.enable_relinearization(ork)
+    gm.enable_relinearization(grk)
+    got = gm.multiply(A, B).to_host()
+    for i in range(count):
+        assert (got[i] == om.multiply(octa[i], octb[i]).to_array()).all()
+    # + modulus switching (mul.rs:411-416)
+    om.enable_mod_switching()
+    gm.enable_mod_switching()
+    out = gm.multiply(A, B)
+    assert out.level == 1 and len(out) == 2
+    got = out.to_host()
+    for i in range(count):
+        assert (got[i] == om.multiply(octa[i], octb[i]).to_array()).all()
+    # without relinearization but with modulus switching: three parts one level down
+    om2 = oracle.Multiplicator(opar, oracle.ScalingFactor.one(), oracle.ScalingFactor(P, Q), basis,
+                               oracle.ScalingFactor(t, P))
+    om2.enable_mod_switching()
+    gm2 = F.Multiplicator.new(F.ScalingFactor.one(), F.ScalingFactor(P, Q), basis, F.ScalingFactor(t, P), gpar)
+    gm2.enable_mod_switching()
+    out = gm2.multiply(A, B)
+    assert out.level == 1 and len(out) == 3
+    got = out.to_host()
+    for i in range(count):
+        assert (got[i] == om2.multiply(octa[i], octb[i]).to_array()).all()
+    # the default strategy through the custom entry point == the fused default path
+    dflt = gpar.mul_basis(0)
+    gd = F.Multiplicator.new(F.ScalingFactor.one(), F.ScalingFactor.one(), dflt, F.ScalingFactor(t, Q), gpar)
+    gd.enable_relinearization(grk)
+    assert (gd.multiply(A, B).to_host() == F.Multiplicator.default(grk).multiply(A, B).to_host()).all()
+    # both extenders with a non-unit factor (no common prefix on either side), non-62-bit extra prime in the basis
+    basis3 = basis + [oracle.generate_prime(50, 2 * degree, 1 << 50)]
+    P3 = P * basis3[-1]
+    om3 = oracle.Multiplicator(opar, oracle.ScalingFactor(3, 1), oracle.ScalingFactor(P3, 3 * Q), basis3,
+                               oracle.ScalingFactor(t, P3))
+    gm3 = F.Multiplicator.new(F.ScalingFactor(3, 1), F.ScalingFactor(P3, 3 * Q), basis3, F.ScalingFactor(t, P3), gpar)
+    got = gm3.multiply(A, B).to_host()
+    for i in range(count):
+        assert (got[i] == om3.multiply(octa[i], octb[i]).to_array()).all()
+    # error behaviour
+    with pytest.raises(F.FheError) as e:   # level out of range (context_at_level)
+        F.Multiplicator.new_leveled(F.ScalingFactor.one(), F.ScalingFactor.one(), dflt, F.ScalingFactor(t, Q), nmod, gpar)
+    assert e.value.code == -6
+    with pytest.raises(F.FheError) as e:   # duplicate modulus in the basis
+        F.Multiplicator.new(F.ScalingFactor.one(), F.ScalingFactor.one(), dflt + [dflt[0]], F.ScalingFactor(t, Q), gpar)
+    assert e.value.code == -2
+    with pytest.raises(F.FheError) as e:   # not NTT friendly
+        F.Multiplicator.new(F.ScalingFactor.one(), F.ScalingFactor.one(), dflt + [113], F.ScalingFactor(t, Q), gpar)
+    assert e.value.code == -4
+
+
+@pytest.mark.parametrize("degree,nmod", [(16, 3), (64, 2), (4096, 2)])
 def test_galois_and_key_switch(oracle, F, degree, nmod):
     """GaloisKey::relinearize (galois_key.rs:63-86), Poly::substitute (rq/mod.rs:360-389),
     KeySwitchingKey::key_switch (key_switching_key.rs:241-270), rotation semantics (:211-230)."""

@@ -269,6 +269,36 @@ def test_multiply_decrypts_to_product(oracle, nmod):
     assert (sk.decrypt(cta.neg()) == (1153 - a) % 1153).all()
 
 
+def test_second_multiplication_strategy(oracle):
+    """ops/mul.rs:369-418 `different_mul_strategy`: the second strategy of ePrint 2021/204 (rhs scaled by P/Q into the
+    extended basis, product scaled by t/P), built with Multiplicator::new; decrypts to the product with and without
+    modulus switching."""
+    rng = np.random.default_rng(204)
+    t = 1153
+    par = oracle.BfvParameters(16, t, moduli_sizes=[62] * 3)
+    basis = list(par.moduli)
+    for _ in range(3):
+        basis.append(oracle.generate_prime(62, 2 * par.degree, basis[-1]))
+    P = 1
+    for q in basis[3:]:
+        P *= q
+    Q = par.context_at_level(0).modulus()
+    for _ in range(3):
+        sk = oracle.SecretKey(par, rng)
+        a = rng.integers(0, t, 16)
+        ct1, ct2 = sk.encrypt(a, 0, rng), sk.encrypt(a, 0, rng)
+        m = oracle.Multiplicator(par, oracle.ScalingFactor.one(), oracle.ScalingFactor(P, Q), basis,
+                                 oracle.ScalingFactor(t, P))
+        assert m.extender_lhs.number_common_moduli == 3 and m.extender_rhs.number_common_moduli == 0
+        ct3 = m.multiply(ct1, ct2)
+        assert len(ct3.c) == 3
+        exp = _negacyclic(a, a, t)
+        assert (sk.decrypt(ct3) == exp).all()
+        m.enable_mod_switching()
+        ct3 = m.multiply(ct1, ct2)
+        assert ct3.level == 1 and (sk.decrypt(ct3) == exp).all()
+
+
 def test_key_switch_noise_and_galois(oracle):
     """key_switching_key.rs:532-560 (noise <= 70 bits), galois_key.rs:211-230 (slot permutation)"""
     rng = np.random.default_rng(21)
