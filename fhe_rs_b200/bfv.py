@@ -20,7 +20,7 @@ from . import _capi
 from ._capi import NTT, POWER_BASIS, FheError, check
 
 __all__ = ["BfvParameters", "BfvParametersBuilder", "Ciphertext", "KeySwitchingKey", "RelinearizationKey", "RGSWCiphertext",
-           "GaloisKey", "EvaluationKey", "Multiplicator", "ScalingFactor", "FheError", "NTT", "POWER_BASIS"]
+           "GaloisKey", "EvaluationKey", "Multiplicator", "ScalingFactor", "dot_product_scalar", "FheError", "NTT", "POWER_BASIS"]
 
 
 def _ptr(a: np.ndarray) -> int:
@@ -505,6 +505,29 @@ class EvaluationKey:
         if e not in self.gk:
             raise FheError(_capi.INVALID_ARGUMENT, "EvaluationKeyError: column rotation not supported by this key")
         return self.gk[e].relinearize(ct)
+
+
+def dot_product_scalar(cts: "Ciphertext", pts, n_terms: Optional[int] = None) -> "Ciphertext":
+    """fhe::bfv::dot_product_scalar (bfv/ops/dot_product.rs:55-184): sum_i cts[i] * pts[i].
+
+    `cts` is a batch of ciphertexts, `pts` a batch of NTT plaintext polynomials (a one-part `Ciphertext` batch, or
+    u64 words [count][limbs][N] = Plaintext::poly_ntt).  With `n_terms` smaller than the batch, the call computes
+    count / n_terms independent dot products at once; an operand holding exactly n_terms entries is shared by all of
+    them (the expanded PIR query of examples/mulpir.rs:153-181)."""
+    if not isinstance(pts, Ciphertext):
+        w = np.ascontiguousarray(pts, dtype=np.uint64)
+        if w.ndim != 3:
+            raise FheError(_capi.INVALID_ARGUMENT, "expected [count][limbs][N] plaintext words")
+        if w.shape[0] == 0:
+            raise FheError(_capi.INVALID_ARGUMENT, "DotProductError::EmptyInput")
+        pts = Ciphertext.from_host(cts.par, w[:, None], cts.level, NTT, cts.stream)
+    n = n_terms if n_terms is not None else max(cts.count, pts.count)
+    if n <= 0:
+        raise FheError(_capi.INVALID_ARGUMENT, "DotProductError::EmptyInput")
+    groups = max(cts.count, pts.count) // n
+    out = Ciphertext(cts.par, max(groups, 1), len(cts), cts.level, NTT, cts.stream)
+    check(_capi.lib().fhe_b200_dot_product_scalar(cts._h, pts._h, n, out._h, cts.stream))
+    return out
 
 
 class ScalingFactor:

@@ -756,6 +756,28 @@ int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n
   API_END
 }
 
+int fhe_b200_dot_product_scalar(const fhe_b200_batch* cts, const fhe_b200_batch* pts, uint32_t n_terms,
+                                fhe_b200_batch* out, void* stream) {
+  API_BEGIN
+  REQUIRE(cts && pts && out, FHE_B200_INVALID_ARGUMENT, "null argument");
+  REQUIRE(n_terms > 0 && cts->count > 0 && pts->count > 0, FHE_B200_INVALID_ARGUMENT, "DotProductError::EmptyInput");
+  check_same(cts, pts);
+  check_same(cts, out);
+  REQUIRE(pts->parts == 1, FHE_B200_BAD_POLY_COUNT, "plaintext batch must hold one polynomial per entry");
+  REQUIRE(out->parts == cts->parts, FHE_B200_BAD_POLY_COUNT, "DotProductError::CiphertextPolynomialCountMismatch");
+  const size_t total = (size_t)out->count * n_terms;
+  REQUIRE((cts->count == total || cts->count == n_terms) && (pts->count == total || pts->count == n_terms),
+          FHE_B200_INVALID_ARGUMENT, "DotProductError::OperandCountMismatch");
+  need_repr(cts, FHE_B200_NTT);
+  need_repr(pts, FHE_B200_NTT);
+  DeviceGuard g(cts->par);
+  launch_dot(cts->d, pts->d, out->d, out->count, n_terms, cts->parts, cts->count, pts->count, ids_of(cts),
+             cts->par->d_limbs, cts->par->logn, (cudaStream_t)stream);
+  FHE_CUDA(cudaGetLastError());
+  out->repr = FHE_B200_NTT;
+  API_END
+}
+
 int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batch* out3, void* stream) {
   API_BEGIN
   REQUIRE(a && b && out3, FHE_B200_INVALID_ARGUMENT, "null argument");

@@ -40,6 +40,11 @@ void launch_ew(EwOp op, u64* a, const u64* b, size_t n_rows, const RowIds& ids, 
 void launch_mul_plain(u64* a, const u64* pt, u32 cts, u32 parts, u32 n_pt, const RowIds& ids, const LimbDev* limbs,
                       u32 logn, cudaStream_t st);
 
+// dot_product_scalar (bfv/ops/dot_product.rs:55-184): out[g] = sum_{i<n_terms} ct[(g*n+i) % ct_count] (.) pt[(g*n+i) % pt_count]
+// ct: [ct_count][parts][limbs][N], pt: [pt_count][limbs][N], out: [groups][parts][limbs][N], all NTT
+void launch_dot(const u64* ct, const u64* pt, u64* out, u32 groups, u32 n_terms, u32 parts, u32 ct_count,
+                u32 pt_count, const RowIds& ids, const LimbDev* limbs, u32 logn, cudaStream_t st);
+
 // tensor product of two 2-part ciphertexts over the multiplication basis (mul.rs:198-201).
 // a,b: [ct][2][L][N] NTT (supply the first nca / ncb mul-basis limbs of their side: the common prefix a factor-one
 // extender keeps); xa: [ct][2][K-nca][N], xb: [ct][2][K-ncb][N] (the scaled limbs, NTT); out: [ct][3][K][N].

@@ -63,6 +63,46 @@ __global__ void mul_plain_kernel(MulPlainArgs A) {
   A.a[idx] = mulmod_limb(A.a[idx], w, M);
 }
 
+// ------------------------------------------------------------------ dot_product_scalar
+struct DotArgs {
+  const u64 *ct, *pt;
+  u64* out;
+  u32 groups, n_terms, parts, ct_count, pt_count, limbs_per_poly, logn;
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+// out[g][part][limb][:] = sum_i ct[(g*n + i) % ct_count][part][limb][:] * pt[(g*n + i) % pt_count][limb][:]
+// (bfv/ops/dot_product.rs:55-184: u128 fused multiply-adds per coefficient, one reduction at the end; the lazy
+// register here is 160 bits wide, so no term-count threshold / fallback path is needed).  HBM-bound: two words
+// read per multiply; two terms in flight per trip.
+__global__ void dot_kernel(DotArgs A) {
+  const u32 N = 1u << A.logn;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over groups*parts*limbs*N
+  size_t total = ((size_t)A.groups * A.parts * A.limbs_per_poly) << A.logn;
+  if (idx >= total) return;
+  const u32 c = idx & (N - 1);
+  size_t row = idx >> A.logn;
+  const u32 limb = row % A.limbs_per_poly;
+  row /= A.limbs_per_poly;
+  const u32 part = row % A.parts, g = (u32)(row / A.parts);
+  const LimbDev& M = A.limbs[A.ids[limb]];
+  const size_t ct_stride = ((size_t)A.parts * A.limbs_per_poly) << A.logn, pt_stride = (size_t)A.limbs_per_poly << A.logn;
+  const u64* cp = A.ct + (((size_t)part * A.limbs_per_poly + limb) << A.logn) + c;
+  const u64* pp = A.pt + ((size_t)limb << A.logn) + c;
+  Acc192 acc;
+  acc.clear();
+  const size_t i0 = (size_t)g * A.n_terms;
+  u32 i = 0;
+  for (; i + 2 <= A.n_terms; i += 2) {
+    const u64 x0 = cp[((i0 + i) % A.ct_count) * ct_stride], x1 = cp[((i0 + i + 1) % A.ct_count) * ct_stride];
+    const u64 y0 = pp[((i0 + i) % A.pt_count) * pt_stride], y1 = pp[((i0 + i + 1) % A.pt_count) * pt_stride];
+    acc.mac(x0, y0);
+    acc.mac(x1, y1);
+  }
+  if (i < A.n_terms) acc.mac(cp[((i0 + i) % A.ct_count) * ct_stride], pp[((i0 + i) % A.pt_count) * pt_stride]);
+  A.out[idx] = acc.reduce(M);
+}
+
 // ------------------------------------------------------------------ tensor
 struct TensorArgs {
   const u64 *a, *b, *xa, *xb;
@@ -572,6 +612,19 @@ void launch_mul_plain(u64* a, const u64* pt, u32 cts, u32 parts, u32 n_pt, const
   size_t total = ((size_t)cts * parts * ids.limbs_per_poly) << logn;
   if (!total) return;
   mul_plain_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+  g_launches++;
+}
+
+void launch_dot(const u64* ct, const u64* pt, u64* out, u32 groups, u32 n_terms, u32 parts, u32 ct_count,
+                u32 pt_count, const RowIds& ids, const LimbDev* limbs, u32 logn, cudaStream_t st) {
+  DotArgs A;
+  A.ct = ct; A.pt = pt; A.out = out; A.groups = groups; A.n_terms = n_terms; A.parts = parts;
+  A.ct_count = ct_count; A.pt_count = pt_count; A.logn = logn;
+  A.limbs_per_poly = ids.limbs_per_poly; A.limbs = limbs;
+  copy_ids(A.ids, ids);
+  size_t total = ((size_t)groups * parts * ids.limbs_per_poly) << logn;
+  if (!total) return;
+  dot_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
   g_launches++;
 }
 

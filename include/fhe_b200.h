@@ -136,6 +136,13 @@ int fhe_b200_neg(fhe_b200_batch* a, void* stream);
  * ciphertext is multiplied coefficient-wise by an NTT-domain polynomial.  host_polys holds n_polys polynomials of
  * [limbs][N] words (Plaintext::poly_ntt, or a monomial of EvaluationKey::expands); n_polys is 1 (shared) or count. */
 int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, void* stream);
+/* dot_product_scalar (bfv/ops/dot_product.rs:55-184): out[g] = sum_{i < n_terms} cts[g*n_terms + i] (.) pts[g*n_terms + i]
+ * for g < out.count.  pts is a batch with one NTT polynomial per entry (Plaintext::poly_ntt); either operand may hold
+ * n_terms entries only, shared by every group (the PIR loops of examples/mulpir.rs:153-181 share the expanded query
+ * across database columns), or out.count * n_terms.  Errors: EmptyInput / OperandCountMismatch -> INVALID_ARGUMENT,
+ * CiphertextPolynomialCountMismatch -> BAD_POLY_COUNT, mixed levels -> INVALID_LEVEL. */
+int fhe_b200_dot_product_scalar(const fhe_b200_batch* cts, const fhe_b200_batch* pts, uint32_t n_terms,
+                                fhe_b200_batch* out, void* stream);
 /* &Ciphertext * &Ciphertext, 2 parts x 2 parts -> 3 parts (bfv/ops/mod.rs:259-358) */
 int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batch* out3, void* stream);
 /* RelinearizationKey::relinearizes: (c0,c1,c2) -> (c0,c1) (keys/relinearization_key.rs:70-103) */

@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <algorithm>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -244,6 +245,17 @@ class EvaluationKey {
   std::shared_ptr<BfvParameters> par_;
   std::map<uint32_t, std::shared_ptr<GaloisKey>> gk_;
 };
+
+// fhe::bfv::dot_product_scalar (bfv/ops/dot_product.rs:55): out[g] = sum_{i<n_terms} cts[g*n_terms+i] * pts[g*n_terms+i];
+// pts is a batch of one-part NTT polynomials (Plaintext::poly_ntt).  An operand with exactly n_terms entries is shared
+// by every group.
+inline Ciphertext dot_product_scalar(const Ciphertext& cts, const Ciphertext& pts, uint32_t n_terms) {
+  if (n_terms == 0) throw Error(FHE_B200_INVALID_ARGUMENT, "DotProductError::EmptyInput");
+  const uint32_t groups = std::max(cts.count(), pts.count()) / n_terms;
+  Ciphertext out(cts.par(), groups ? groups : 1, cts.len(), cts.level(), Representation::Ntt, cts.stream());
+  check(fhe_b200_dot_product_scalar(cts.handle(), pts.handle(), n_terms, out.handle(), cts.stream()));
+  return out;
+}
 
 // fhe_math::rns::ScalingFactor (rns/scaler.rs:20-58): numerator / denominator as little-endian byte strings
 // (BigUint::to_bytes_le)

@@ -1118,6 +1118,34 @@ class GaloisKey:
         return Ciphertext(ct.par, [c0, c1], self.ksk.ciphertext_level)
 
 
+def dot_product_scalar(cts: Sequence["Ciphertext"], pts: Sequence["Poly"]) -> "Ciphertext":
+    """bfv/ops/dot_product.rs:55-184: sum_i ct_i (.) pt_i with wide accumulators and one reduction per coefficient
+    (both branches of the reference -- u128 fma below the 2^(2*lz) term threshold, rq::dot_product above it -- give the
+    canonical residue of the exact sum)."""
+    cts, pts = list(cts), list(pts)
+    if not cts or not pts:
+        raise ValueError("EmptyInput")
+    if len(cts) != len(pts):
+        raise ValueError("OperandCountMismatch")
+    first = cts[0]
+    ctx = first.par.context_at_level(first.level)
+    for ct, pt in zip(cts, pts):
+        if ct.level != first.level or pt.ctx != ctx or pt.rep != NTT:
+            raise ValueError("InvalidLevel")
+        if len(ct.c) != len(first.c):
+            raise ValueError("CiphertextPolynomialCountMismatch")
+    out = []
+    for part in range(len(first.c)):
+        acc = np.zeros((len(ctx.moduli), first.par.degree), dtype=object)
+        for ct, pt in zip(cts, pts):
+            acc += ct.c[part].c.astype(object) * pt.c.astype(object)
+        rows = np.zeros(acc.shape, np.uint64)
+        for i, q in enumerate(ctx.moduli):
+            rows[i] = np.array([int(v) % q for v in acc[i]], dtype=np.uint64)
+        out.append(Poly(ctx, NTT, rows))
+    return Ciphertext(first.par, out, first.level)
+
+
 def computes_inner_sum(par: BfvParameters, gks: dict, ct: Ciphertext) -> Ciphertext:
     """EvaluationKey::computes_inner_sum, evaluation_key.rs:56-100 (gks: exponent -> GaloisKey)."""
     out = ct.copy()

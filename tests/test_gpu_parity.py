@@ -488,6 +488,53 @@ def test_wire_format(oracle, F, degree, sizes):
         F.Ciphertext.from_packed(gpar, zb[:, :, :-1], repr=F.NTT)
 
 
+@pytest.mark.parametrize("degree,nmod,n_terms,groups", [(16, 2, 1, 1), (16, 3, 7, 3), (64, 2, 20, 2), (4096, 2, 5, 2)])
+def test_dot_product_scalar(oracle, F, degree, nmod, n_terms, groups):
+    """dot_product_scalar (bfv/ops/dot_product.rs:55-184, tests :186-260): bit-exact against the oracle for several
+    independent dot products per call, with the ciphertext or the plaintext operand shared across them, on 2- and
+    3-part ciphertexts; error behaviour of the reference."""
+    t = 1153
+    opar, gpar, rng = make_pair(oracle, F, degree, nmod, t, 31 + n_terms)
+    ctx = opar.context_at_level(0)
+    for parts in (2, 3):
+        carr = rand_ct(oracle, opar, rng, groups * n_terms, parts)
+        parr = rand_ct(oracle, opar, rng, groups * n_terms, 1)[:, 0]
+        octs = [oracle.Ciphertext.from_array(opar, a, 0) for a in carr]
+        opts = [oracle.Poly(ctx, oracle.NTT, a.copy()) for a in parr]
+        X = F.Ciphertext.from_host(gpar, carr)
+        got = F.dot_product_scalar(X, parr, n_terms).to_host()
+        assert got.shape[0] == groups
+        for g in range(groups):
+            sl = slice(g * n_terms, (g + 1) * n_terms)
+            assert (got[g] == oracle.dot_product_scalar(octs[sl], opts[sl]).to_array()).all()
+        # shared ciphertexts (the PIR query), per-group plaintexts; then the other way round
+        Xs = F.Ciphertext.from_host(gpar, carr[:n_terms])
+        got = F.dot_product_scalar(Xs, parr, n_terms).to_host()
+        for g in range(groups):
+            sl = slice(g * n_terms, (g + 1) * n_terms)
+            assert (got[g] == oracle.dot_product_scalar(octs[:n_terms], opts[sl]).to_array()).all()
+        got = F.dot_product_scalar(X, parr[:n_terms], n_terms).to_host()
+        for g in range(groups):
+            sl = slice(g * n_terms, (g + 1) * n_terms)
+            assert (got[g] == oracle.dot_product_scalar(octs[sl], opts[:n_terms]).to_array()).all()
+    # one dot product over the whole batch (n_terms defaults to the batch size)
+    got = F.dot_product_scalar(X, parr).to_host()
+    assert got.shape[0] == 1 and (got[0] == oracle.dot_product_scalar(octs, opts).to_array()).all()
+    # errors (dot_product.rs:60-70, :93-101)
+    with pytest.raises(F.FheError) as e:
+        F.dot_product_scalar(X, np.zeros((0, nmod, degree), np.uint64))
+    assert e.value.code == -1
+    if groups * n_terms > 2:
+        with pytest.raises(F.FheError) as e:   # operand counts do not match
+            F.dot_product_scalar(X, parr[:groups * n_terms - 1], groups * n_terms)
+        assert e.value.code == -1
+    if nmod >= 2:
+        with pytest.raises(F.FheError) as e:   # plaintext at another level
+            lower = F.Ciphertext(gpar, groups * n_terms, 1, level=1)
+            F.dot_product_scalar(X, lower, n_terms)
+        assert e.value.code == -6
+
+
 def test_mul_plain_inner_sum_expand(oracle, F):
     """Ciphertext * Plaintext (ops/mod.rs:229-238), EvaluationKey::computes_inner_sum (evaluation_key.rs:56-100)
     and EvaluationKey::expands (:192-256) -- the PIR examples' loops, built from the same kernels"""

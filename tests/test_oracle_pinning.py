@@ -299,6 +299,33 @@ def test_second_multiplication_strategy(oracle):
         assert ct3.level == 1 and (sk.decrypt(ct3) == exp).all()
 
 
+def test_dot_product_scalar(oracle):
+    """bfv/ops/dot_product.rs:186-260 `test_dot_product_scalar`: empty input is an error; the result equals the sum of
+    the ct * pt products and decrypts to the SIMD dot product."""
+    rng = np.random.default_rng(77)
+    t = 1153
+    par = oracle.BfvParameters(16, t, moduli_sizes=[62] * 2)
+    with pytest.raises(ValueError):
+        oracle.dot_product_scalar([], [])
+    sk = oracle.SecretKey(par, rng)
+    for size in (1, 2, 7, 20):
+        vals_c = rng.integers(0, t, size=(size, 16))
+        vals_p = rng.integers(0, t, size=(size, 16))
+        cts = [sk.encrypt(oracle.simd_encode(par, v), 0, rng) for v in vals_c]
+        ctx = par.context_at_level(0)   # Plaintext::poly_ntt: the encoded message itself, transformed (no delta)
+        pts = [oracle.Poly.from_u64(ctx, oracle.simd_encode(par, v), oracle.NTT) for v in vals_p]
+        r = oracle.dot_product_scalar(cts, pts)
+        exp = None
+        for c, p in zip(cts, pts):
+            term = oracle.Ciphertext(par, [x.mul(p) for x in c.c], 0)
+            exp = term if exp is None else exp.add(term)
+        assert (r.to_array() == exp.to_array()).all()
+        dec = oracle.simd_decode(par, sk.decrypt(r))
+        assert (dec.astype(np.int64) == (vals_c * vals_p).sum(axis=0) % t).all()
+    with pytest.raises(ValueError):
+        oracle.dot_product_scalar(cts, pts[:-1])
+
+
 def test_key_switch_noise_and_galois(oracle):
     """key_switching_key.rs:532-560 (noise <= 70 bits), galois_key.rs:211-230 (slot permutation)"""
     rng = np.random.default_rng(21)
