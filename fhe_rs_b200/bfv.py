@@ -309,8 +309,8 @@ class Ciphertext:
         return out
 
     def __mul__(self, rhs: "Ciphertext") -> "Ciphertext":
-        """&Ciphertext * &Ciphertext -> 3-part ciphertext, no relinearization (ops/mod.rs:259-358)."""
-        out = self._like(parts=3)
+        """&Ciphertext * &Ciphertext, no relinearization (ops/mod.rs:259-358): n x m parts -> n + m - 1 parts."""
+        out = self._like(parts=len(self) + len(rhs) - 1)
         check(_capi.lib().fhe_b200_mul(self._h, rhs._h, out._h, self.stream))
         return out
 

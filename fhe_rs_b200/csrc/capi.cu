@@ -396,6 +396,31 @@ void mul_core(const fhe_b200_params* par, const LevelData& lv, const u64* a, con
   launch_scale(lv.down.dev, par->d_limbs, T, out0, out1, cts * 3, L, 0, L, split, logn, st);
 }
 
+// &ct * &ct for any part counts (ops/mod.rs:259-358): out [cts][na+nb-1][L][N] power basis
+void mul_core_parts(const fhe_b200_params* par, const LevelData& lv, const u64* a, u32 na, const u64* b, u32 nb, u32 cts,
+                    u64* out, Workspace& ws, cudaStream_t st) {
+  const u32 L = lv.L, E = lv.E, K = lv.K, logn = par->logn, nc = na + nb - 1;
+  const size_t row = (size_t)1 << logn;
+  RowIds ext_ids;
+  std::memset(&ext_ids, 0, sizeof(ext_ids));
+  ext_ids.limbs_per_poly = E;
+  for (u32 j = 0; j < E; j++) ext_ids.ids[j] = lv.mul_ids.ids[L + j];
+  const u64* src[2] = {a, b};
+  const u32 np[2] = {na, nb};
+  u64* X[2];
+  for (int s = 0; s < 2; s++) {
+    u64* pb = ws.words((size_t)cts * np[s] * L * row);
+    X[s] = ws.words((size_t)cts * np[s] * E * row);
+    launch_ntt(src[s], pb, cts * np[s] * L, lv.ctx_ids, par->d_limbs, logn, true, 1, false, st);
+    launch_scale(lv.ext.dev, par->d_limbs, pb, X[s], nullptr, cts * np[s], E, L, E, 0, logn, st);
+    launch_ntt(X[s], X[s], cts * np[s] * E, ext_ids, par->d_limbs, logn, false, 1, false, st);
+  }
+  u64* T = ws.words((size_t)cts * nc * K * row);
+  launch_tensor_nm(a, b, X[0], X[1], T, cts, L, E, na, nb, lv.mul_ids, par->d_limbs, logn, st);
+  launch_ntt(T, T, cts * nc * K, lv.mul_ids, par->d_limbs, logn, true, 1, false, st);
+  launch_scale(lv.down.dev, par->d_limbs, T, out, nullptr, cts * nc, L, 0, L, 0, logn, st);
+}
+
 // The same pipeline for a custom strategy (mul.rs:192-206 with the Scalers of Multiplicator::new): every extender
 // keeps its common prefix only when its factor is one (rq/scaler.rs:35-43), so a side with a non-unit factor gets all
 // K limbs from the exact scaler.  out: [cts][3][L][N] power basis.
@@ -784,8 +809,8 @@ int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batc
   check_same(a, b);
   check_same(a, out3);
   REQUIRE(!a->mul_basis, FHE_B200_CONTEXT_MISMATCH, "PolynomialContextMismatch");
-  REQUIRE(a->parts == 2 && b->parts == 2 && out3->parts == 3, FHE_B200_BAD_POLY_COUNT,
-          "MultiplicationPolynomialCount: expected 2 x 2 -> 3");
+  REQUIRE(a->parts >= 1 && b->parts >= 1 && out3->parts == a->parts + b->parts - 1, FHE_B200_BAD_POLY_COUNT,
+          "MultiplicationPolynomialCount: expected n x m -> n + m - 1 parts");
   REQUIRE(a->count == b->count && a->count == out3->count, FHE_B200_INVALID_ARGUMENT, "batch sizes differ");
   need_repr(a, FHE_B200_NTT);
   need_repr(b, FHE_B200_NTT);
@@ -794,13 +819,17 @@ int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batc
   const fhe_b200_params* par = a->par;
   const LevelData& lv = par->level(a->level);
   const size_t row = (size_t)1 << par->logn;
+  const u32 na = a->parts, nb = b->parts, nc = na + nb - 1;
   for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
     u32 n = std::min(chunk_size(), a->count - c0);
     Workspace ws(st);
-    u64* o = out3->d + (size_t)c0 * 3 * lv.L * row;
-    mul_core(par, lv, a->d + (size_t)c0 * 2 * lv.L * row, b->d + (size_t)c0 * 2 * lv.L * row, n, o, nullptr, 0, ws, st);
+    u64* o = out3->d + (size_t)c0 * nc * lv.L * row;
+    const u64* pa = a->d + (size_t)c0 * na * lv.L * row;
+    const u64* pb = b->d + (size_t)c0 * nb * lv.L * row;
+    if (na == 2 && nb == 2) mul_core(par, lv, pa, pb, n, o, nullptr, 0, ws, st);
+    else mul_core_parts(par, lv, pa, na, pb, nb, n, o, ws, st);
     // rq/scaler.rs:97-115 forward NTT of the scaled result
-    launch_ntt(o, o, n * 3 * lv.L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+    launch_ntt(o, o, n * nc * lv.L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
   }
   FHE_CUDA(cudaGetLastError());
   out3->repr = FHE_B200_NTT;

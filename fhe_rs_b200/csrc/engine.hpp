@@ -51,6 +51,11 @@ void launch_dot(const u64* ct, const u64* pt, u64* out, u32 groups, u32 n_terms,
 void launch_tensor(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 nca,
                    u32 ncb, u32 K, const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st);
 
+// general part counts (ops/mod.rs:259-358): a [ct][na][L][N], b [ct][nb][L][N], xa [ct][na][E][N], xb [ct][nb][E][N]
+// -> out [ct][na+nb-1][K][N], c[k] = sum_{i+j=k} a_i * b_j
+void launch_tensor_nm(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 E, u32 na,
+                      u32 nb, const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st);
+
 // exact RNS scaler (rns/scaler.rs:249-352), tables resident on the device
 struct ScalerDev {
   u32 n_from, n_to, is_one, shift;

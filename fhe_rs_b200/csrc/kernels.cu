@@ -154,6 +154,38 @@ __global__ void tensor_kernel(TensorArgs A) {
   A.out[o + ((size_t)2 * K << A.logn) + c] = c2;
 }
 
+// General part counts of &ct * &ct (bfv/ops/mod.rs:259-358): c[k] = sum_{i+j=k} a_i * b_j over the multiplication
+// basis, one thread per (ciphertext, output part k, limb, coefficient).  a: [ct][na][L][N], xa: [ct][na][E][N] etc.
+struct TensorNmArgs {
+  const u64 *a, *b, *xa, *xb;
+  u64* out;
+  u32 cts, L, E, na, nb, logn;
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+__global__ void tensor_nm_kernel(TensorNmArgs A) {
+  const u32 N = 1u << A.logn, K = A.L + A.E, nc = A.na + A.nb - 1;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over cts*nc*K*N
+  size_t total = ((size_t)A.cts * nc * K) << A.logn;
+  if (idx >= total) return;
+  const u32 c = idx & (N - 1);
+  size_t row = idx >> A.logn;
+  const u32 pos = row % K;
+  row /= K;
+  const u32 k = row % nc, ct = (u32)(row / nc);
+  const LimbDev& M = A.limbs[A.ids[pos]];
+  const bool ext = pos >= A.L;
+  const u32 rows = ext ? A.E : A.L, r = ext ? pos - A.L : pos;
+  const u64* pa = (ext ? A.xa : A.a) + ((((size_t)ct * A.na) * rows + r) << A.logn) + c;
+  const u64* pb = (ext ? A.xb : A.b) + ((((size_t)ct * A.nb) * rows + r) << A.logn) + c;
+  const size_t ps = (size_t)rows << A.logn;
+  Acc192 acc;
+  acc.clear();
+  const u32 lo = k + 1 > A.nb ? k + 1 - A.nb : 0, hi = k < A.na - 1 ? k : A.na - 1;
+  for (u32 i = lo; i <= hi; i++) acc.mac(pa[i * ps], pb[(k - i) * ps]);
+  A.out[idx] = acc.reduce(M);
+}
+
 // ------------------------------------------------------------------ exact RNS scaler
 struct ScaleArgs {
   ScalerDev S;
@@ -638,6 +670,19 @@ void launch_tensor(const u64* a, const u64* b, const u64* xa, const u64* xb, u64
   size_t total = ((size_t)cts * K) << logn;
   if (!total) return;
   tensor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+  g_launches++;
+}
+
+void launch_tensor_nm(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* out, u32 cts, u32 L, u32 E, u32 na,
+                      u32 nb, const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st) {
+  TensorNmArgs A;
+  A.a = a; A.b = b; A.xa = xa; A.xb = xb; A.out = out;
+  A.cts = cts; A.L = L; A.E = E; A.na = na; A.nb = nb; A.logn = logn;
+  A.limbs = limbs;
+  copy_ids(A.ids, mul_ids);
+  size_t total = ((size_t)cts * (na + nb - 1) * (L + E)) << logn;
+  if (!total) return;
+  tensor_nm_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
   g_launches++;
 }
 

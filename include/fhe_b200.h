@@ -143,7 +143,8 @@ int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n
  * CiphertextPolynomialCountMismatch -> BAD_POLY_COUNT, mixed levels -> INVALID_LEVEL. */
 int fhe_b200_dot_product_scalar(const fhe_b200_batch* cts, const fhe_b200_batch* pts, uint32_t n_terms,
                                 fhe_b200_batch* out, void* stream);
-/* &Ciphertext * &Ciphertext, 2 parts x 2 parts -> 3 parts (bfv/ops/mod.rs:259-358) */
+/* &Ciphertext * &Ciphertext (bfv/ops/mod.rs:259-358): n parts x m parts -> n + m - 1 parts (out3 must have that many;
+ * 2 x 2 -> 3 is the fused path) */
 int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batch* out3, void* stream);
 /* RelinearizationKey::relinearizes: (c0,c1,c2) -> (c0,c1) (keys/relinearization_key.rs:70-103) */
 int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_b200_batch* out2, void* stream);

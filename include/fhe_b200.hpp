@@ -136,7 +136,7 @@ class Ciphertext {
   Ciphertext operator-() const { Ciphertext c = clone(); check(fhe_b200_neg(c.h_, stream_)); return c; }
   // &Ciphertext * &Ciphertext -> 3 parts (bfv/ops/mod.rs:259)
   Ciphertext operator*(const Ciphertext& rhs) const {
-    Ciphertext out(par_, count(), 3, level(), Representation::Ntt, stream_);
+    Ciphertext out(par_, count(), len() + rhs.len() - 1, level(), Representation::Ntt, stream_);
     check(fhe_b200_mul(h_, rhs.h_, out.h_, stream_));
     return out;
   }

@@ -181,6 +181,20 @@ def test_mul_relin_against_oracle(oracle, F, degree, nmod, t):
     assert e.value.code == -6
 
 
+@pytest.mark.parametrize("degree,nmod", [(16, 3), (128, 2)])
+def test_mul_general_part_counts(oracle, F, degree, nmod):
+    """&ct * &ct with n x m parts (ops/mod.rs:259-358: c[i+j] += a_i * b_j over the extended basis), including the
+    product of a 3-part (unrelinearized) ciphertext with a fresh one and a 1-part operand."""
+    opar, gpar, rng = make_pair(oracle, F, degree, nmod, 1153, 77)
+    for na, nb in [(3, 2), (2, 3), (1, 2), (3, 3), (4, 1)]:
+        a, b = rand_ct(oracle, opar, rng, 2, na), rand_ct(oracle, opar, rng, 2, nb)
+        got = (F.Ciphertext.from_host(gpar, a) * F.Ciphertext.from_host(gpar, b)).to_host()
+        assert got.shape[1] == na + nb - 1
+        for i in range(2):
+            exp = oracle.Ciphertext.from_array(opar, a[i], 0).mul(oracle.Ciphertext.from_array(opar, b[i], 0))
+            assert (got[i] == exp.to_array()).all()
+
+
 @pytest.mark.parametrize("degree,nmod", [(16, 3), (64, 2), (4096, 2)])
 def test_custom_multiplication_strategy(oracle, F, degree, nmod):
     """Multiplicator::new / new_leveled (mul.rs:37-98) and the reference's `different_mul_strategy` test
