@@ -79,6 +79,15 @@ struct fhe_b200_params {
     d.to_lo = to_dev(s.h.theta_omega_lo);
     d.to_hi = to_dev(s.h.theta_omega_hi);
     d.to_sign = to_dev(s.h.theta_omega_sign);
+    {
+      std::vector<unsigned char> order;
+      for (int sg = 0; sg < 2; sg++)
+        for (size_t i = 0; i < s.h.theta_omega_sign.size(); i++)
+          if ((int)s.h.theta_omega_sign[i] == sg) order.push_back((unsigned char)i);
+      d.n_pos = 0;
+      for (unsigned char v : s.h.theta_omega_sign) d.n_pos += v == 0;
+      d.to_order = to_dev(order);
+    }
     d.tgar_lo = to_dev(s.h.theta_garner_lo);
     d.tgar_hi = to_dev(s.h.theta_garner_hi);
   }
@@ -207,6 +216,15 @@ struct fhe_b200_multiplicator {
     d.to_lo = to_dev(sd.h.theta_omega_lo);
     d.to_hi = to_dev(sd.h.theta_omega_hi);
     d.to_sign = to_dev(sd.h.theta_omega_sign);
+    {
+      std::vector<unsigned char> order;
+      for (int sg = 0; sg < 2; sg++)
+        for (size_t i = 0; i < sd.h.theta_omega_sign.size(); i++)
+          if ((int)sd.h.theta_omega_sign[i] == sg) order.push_back((unsigned char)i);
+      d.n_pos = 0;
+      for (unsigned char v : sd.h.theta_omega_sign) d.n_pos += v == 0;
+      d.to_order = to_dev(order);
+    }
     d.tgar_lo = to_dev(sd.h.theta_garner_lo);
     d.tgar_hi = to_dev(sd.h.theta_garner_hi);
   }

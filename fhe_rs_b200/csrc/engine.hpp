@@ -66,6 +66,8 @@ struct ScalerDev {
   const u64* to_lo;       // theta_omega [n_from]
   const u64* to_hi;
   const unsigned char* to_sign;
+  const unsigned char* to_order;   // source indices, the theta_omega terms with positive sign first
+  u32 n_pos, pad2;
   const u64* tgar_lo;     // theta_garner [n_from]
   const u64* tgar_hi;
   unsigned short to_ids[kMaxPos];

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   u64* s_tgh = s_tgl + nf;
   u64* s_tol = s_tgh + nf;
   u64* s_toh = s_tol + nf;
-  u64* s_tos = s_toh + nf;
+  u32* s_ord = reinterpret_cast<u32*>(s_toh + nf);   // [n_from] term order of the w sum
 
   const u32 N = 1u << A.logn;
   const u32 per_poly = N / TC;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
     s_tgh[i] = S.tgar_hi[i];
     s_tol[i] = S.to_lo[i];
     s_toh[i] = S.to_hi[i];
-    s_tos[i] = S.to_sign[i];
+    s_ord[i] = S.to_order[i];
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -334,15 +334,18 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   bool w_sign = false;
   u128 w = 0;
   if (!S.is_one) {
-    // one pass per sign (table-driven, CTA-uniform branch) keeps a single accumulator set live
+    // one pass per sign keeps a single accumulator set live; the table lists the positive terms first
     U256 s_pos = {0, 0, 0, 0}, s_neg = {0, 0, 0, 0};
 #pragma unroll 1
     for (u32 sg = 0; sg < 2; sg++) {
       AccTheta at;
       at.clear();
+      const u32 k0 = sg ? S.n_pos : 0, k1 = sg ? nf : S.n_pos;
 #pragma unroll 2
-      for (u32 i = 0; i < nf; i++)
-        if ((u32)s_tos[i] == sg) at.mac(s_r[i * TC + cc], s_tol[i], s_toh[i]);
+      for (u32 k = k0; k < k1; k++) {
+        const u32 i = s_ord[k];
+        at.mac(s_r[i * TC + cc], s_tol[i], s_toh[i]);
+      }
       u32 wds[7];
       at.words(wds);
       if (sg == 0) s_pos = u256_from_acc(wds);
@@ -494,7 +497,9 @@ __global__ void ksmac_kernel(KsMacArgs A) {
   const u64* k1_ptr = A.k1 + ((size_t)j << A.logn) + c;
   const size_t dstride = (size_t)A.Lk << A.logn;
   // two digits per trip, the six words of the next trip requested before the multiplies of this one (the kernel
-  // is bound by HBM latency, not by the multiplier: 2 x n_dig x 8 IMAD.WIDE per 48 bytes read)
+  // is bound by HBM latency, not by the multiplier: 2 x n_dig x 8 IMAD.WIDE per 48 bytes read).  Two
+  // coefficients per thread with 16-byte accesses, and four ciphertexts per thread sharing each key word (a third
+  // of the L2 -> SM bytes), both measured the same or slower: ~3.0 TB/s of HBM reads either way (profiles/microbench_r1.txt)
   u32 i = 0;
   u64 t0 = 0, t1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
   if (A.n_dig >= 2) {
