@@ -338,7 +338,9 @@ void key_switch_core(const fhe_b200_params* par, const fhe_b200_ksk* k, const u6
   for (u32 i = 0; i < L; i++) qmax = std::max(qmax, par->moduli[i]);
   for (u32 j = 0; j < Lk; j++) qmin = std::min(qmin, par->moduli[j]);
   const bool reduce = qmax > 4 * qmin - 1 || qmin < (1ull << 8);
-  launch_ntt(c2, inter, cts * L * Lk, kl.ctx_ids, par->d_limbs, par->logn, false, Lk, reduce, st);
+  // forward_vt_lazy (rq/mod.rs:580): the digits stay in [0,4q_j); the lazy accumulator of the inner product takes
+  // any 64-bit operand and reduces once
+  launch_ntt(c2, inter, cts * L * Lk, kl.ctx_ids, par->d_limbs, par->logn, false, Lk, reduce, st, true);
   launch_ksmac(inter, k->k0, k->k1, base0, base1, out0, out1, cts, L, Lk, out_ct_rows, kl.ctx_ids, par->d_limbs,
                par->logn, st);
 }

@@ -27,9 +27,9 @@ struct RowIds {
 
 // ---- NTT (ntt.cu)
 // Transforms n_rows rows of N words.  in may differ from out (first pass reads in).
-// in_div / reduce_on_load: see NttArgs.
+// in_div / reduce_on_load / lazy_out: see NttArgs.
 void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
-                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st);
+                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out = false);
 
 // ---- element-wise (kernels.cu)
 enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2 };

@@ -85,7 +85,7 @@ void run_cols_for(const NttArgs& a, cudaStream_t st) {
 }  // namespace
 
 void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
-                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st) {
+                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out) {
   if (n_rows == 0) return;
   NttArgs a;
   a.in = in;
@@ -95,6 +95,7 @@ void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const Li
   a.limbs_per_poly = ids.limbs_per_poly;
   a.in_div = in_div;
   a.reduce_on_load = reduce_on_load ? 1 : 0;
+  a.lazy_out = (lazy_out && !inverse) ? 1 : 0;
   a.logn = logn;
   for (int i = 0; i < kMaxPos; i++) a.ids[i] = ids.ids[i];
   if (logn <= 12) {

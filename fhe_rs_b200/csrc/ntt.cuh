@@ -31,6 +31,7 @@ struct NttArgs {
   u32 reduce_on_load;   // reduce source words modulo the row's prime on load
   u32 logn;             // log2 N
   u32 logn1;            // log2 N1 (0 => single-kernel transform done by the rows kernel)
+  u32 lazy_out;         // forward only: leave the outputs in [0,4p) (forward_vt_lazy, ntt/native.rs:142-181)
   unsigned short ids[kMaxPos];  // limb position -> index into `limbs`
 };
 
@@ -229,7 +230,10 @@ __global__ void ntt_rows_kernel(NttArgs A) {
     sm[sm_phys(e)] = v;
   }
   __syncthreads();
-  ntt_tile_transform<LOGP, LOGB, false, INV>(sm, L, (int)A.logn1, A.logn, tile << LOGB, A.logn1 == 0);
+  // the transforms compare `stage == logn` to find the last stage, where the outputs are fully reduced; a lazy
+  // forward transform never meets that condition
+  ntt_tile_transform<LOGP, LOGB, false, INV>(sm, L, (int)A.logn1, (!INV && A.lazy_out) ? 0xffu : A.logn, tile << LOGB,
+                                             A.logn1 == 0);
   for (u32 e = threadIdx.x; e < P * R; e += blockDim.x) dst[e] = sm[sm_phys(e)];
 }
 

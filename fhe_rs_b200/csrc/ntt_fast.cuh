@@ -280,7 +280,9 @@ __global__ void __launch_bounds__(512, 2) ntt_fast_kernel(NttArgs A) {
   }
   const LimbDev& L = A.limbs[A.ids[row % A.limbs_per_poly]];
   const bool first_pass = COLS || A.logn1 == 0;
-  FastTile<LOGP, COLS, INV, false>::run(src, dst, gstride_a, sm, A.reduce_on_load != 0, L, s_base, A.logn, row0, first_pass);
+  // (a lazy forward transform never meets the `stage == logn` test that selects the fully reducing last stage)
+  FastTile<LOGP, COLS, INV, false>::run(src, dst, gstride_a, sm, A.reduce_on_load != 0, L, s_base,
+                                        (!INV && A.lazy_out) ? 0xffu : A.logn, row0, first_pass);
 }
 
 }  // namespace fhe_b200
