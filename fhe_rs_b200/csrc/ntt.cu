@@ -31,26 +31,26 @@ void run_cols(const NttArgs& a, cudaStream_t st) {
   g_launches++;
 }
 
-template <int LOGP, bool COLS, bool INV>
+template <int LOGP, bool COLS, bool INV, int TLOG = 12>
 void run_fast(const NttArgs& a, cudaStream_t st) {
-  constexpr size_t smem = 2 * 4672 * sizeof(u64);
+  constexpr size_t smem = 2 * FastTile<LOGP, COLS, INV, false, TLOG>::TW * sizeof(u64);
   static bool configured = false;  // per instantiation
   if (!configured) {
-    cudaFuncSetAttribute(ntt_fast_kernel<LOGP, COLS, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(ntt_fast_kernel<LOGP, COLS, INV, TLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  constexpr int LOGB = 12 - LOGP;
+  constexpr int LOGB = TLOG - LOGP;
   const u32 tiles = COLS ? ((1u << (a.logn - LOGP)) >> LOGB) : ((1u << a.logn1) >> LOGB);
-  ntt_fast_kernel<LOGP, COLS, INV><<<a.n_rows * tiles, 512, smem, st>>>(a);
+  ntt_fast_kernel<LOGP, COLS, INV, TLOG><<<a.n_rows * tiles, 1 << (TLOG - 3), smem, st>>>(a);
   g_launches++;
 }
-template <bool INV>
+template <bool INV, int TLOG = 12>
 void run_fast_cols_for(const NttArgs& a, cudaStream_t st) {
   switch (a.logn1) {
-    case 7: run_fast<7, true, INV>(a, st); break;
-    case 8: run_fast<8, true, INV>(a, st); break;
-    case 9: run_fast<9, true, INV>(a, st); break;
-    case 10: run_fast<10, true, INV>(a, st); break;
+    case 7: run_fast<7, true, INV, TLOG>(a, st); break;
+    case 8: run_fast<8, true, INV, TLOG>(a, st); break;
+    case 9: run_fast<9, true, INV, TLOG>(a, st); break;
+    case 10: run_fast<10, true, INV, TLOG>(a, st); break;
     default: break;
   }
 }
@@ -122,12 +122,28 @@ void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const Li
     }
     return;
   }
+  // Tile sizes.  Smaller CTAs (same 8 words and <= 64 registers per thread, so the same number of resident warps)
+  // put more independent CTAs on an SM; their load / butterfly / exchange phases interleave and the multiplier
+  // pipe idles less: measured at set C, 4096-word tiles for both passes 3590 products/s, rows pass 2048 words 3710,
+  // 1024 words 3810 (512 words: no further gain), + cols pass 2048 words 3835 (1024 words, i.e. 16-byte column
+  // segments at N = 2^15: 3600).  FHE_B200_ROWS_TLOG / FHE_B200_COLS_TLOG = 12 select the 4096-word tiles.
+  static const int rows_tlog = getenv("FHE_B200_ROWS_TLOG") ? atoi(getenv("FHE_B200_ROWS_TLOG")) : 10;
+  static const int cols_tlog = getenv("FHE_B200_COLS_TLOG") ? atoi(getenv("FHE_B200_COLS_TLOG")) : 11;
+  auto rows = [&](const NttArgs& x, bool inv) {
+    if (rows_tlog == 10) { if (inv) run_fast<6, false, true, 10>(x, st); else run_fast<6, false, false, 10>(x, st); }
+    else { if (inv) run_fast<6, false, true>(x, st); else run_fast<6, false, false>(x, st); }
+  };
+  auto cols = [&](const NttArgs& x, bool inv) {
+    // (N = 2^16 would leave a 2048-word tile two columns wide: keep the 4096-word tile there)
+    if (cols_tlog == 11 && x.logn1 <= 9) { if (inv) run_fast_cols_for<true, 11>(x, st); else run_fast_cols_for<false, 11>(x, st); }
+    else { if (inv) run_fast_cols_for<true>(x, st); else run_fast_cols_for<false>(x, st); }
+  };
   if (!inverse) {
-    run_fast_cols_for<false>(a, st);
-    run_fast<6, false, false>(second, st);
+    cols(a, false);
+    rows(second, false);
   } else {
-    run_fast<6, false, true>(a, st);
-    run_fast_cols_for<true>(second, st);
+    rows(a, true);
+    cols(second, true);
   }
 }
 

@@ -1,5 +1,5 @@
-// Register-resident variant of the two tile kernels of ntt.cuh for N >= 2^13 (4096-word tiles,
-// 512 threads, 8 words per thread).  Same transform, same tables, same outputs; what changes is
+// Register-resident variant of the two tile kernels of ntt.cuh for N >= 2^13 (2^TLOG-word tiles,
+// 2^(TLOG-3) threads, 8 words per thread; TLOG = 10 for the rows pass, 11 for the cols pass, see ntt.cu).  Same transform, same tables, same outputs; what changes is
 // the data movement, tuned to the measured B200 issue limits (profiles/ntt_r1: the ALU pipe --
 // address arithmetic, selects, carries -- not HBM, bounds the NTT):
 //   * the first round reads its 8 words straight from global memory into registers and the last
@@ -16,14 +16,16 @@ namespace fhe_b200 {
 // offset of element `je` (stride S words) of a radix group relative to the padded base
 __host__ __device__ constexpr u32 pad_delta(u32 je, u32 S) { return je * S + ((je * S) >> 5); }
 
-// LOGP: log2 points of the in-tile transform; LOGB = 12 - LOGP batch lanes; COLS layout as in ntt.cuh.
-template <int LOGP, bool COLS, bool INV, bool SOL>
+// LOGP: log2 points of the in-tile transform; TLOG: log2 words per tile (8 words per thread, 2^(TLOG-3) threads);
+// LOGB = TLOG - LOGP batch lanes; COLS layout as in ntt.cuh.
+template <int LOGP, bool COLS, bool INV, bool SOL, int TLOG = 12>
 struct FastTile {
-  static constexpr int LOGB = 12 - LOGP;
+  static constexpr int LOGB = TLOG - LOGP;
+  static constexpr u32 NT = 1u << (TLOG - 3);
   static constexpr u32 P = 1u << LOGP, B = 1u << LOGB;
   static constexpr int NR = (LOGP + 2) / 3;
   static constexpr int REM = LOGP - 3 * (NR - 1);
-  static constexpr u32 TW = 4672;  // padded words per tile buffer (>= 4096 + 512 + 8)
+  static constexpr u32 TW = (1u << TLOG) + (1u << (TLOG - 3)) + 64;  // padded words per tile buffer (4672 for 4096)
   // Shared-memory padding.  cols layout: i + i/32.  rows layout with 64-point rows: i + 8*(i/64) + (i/8)%8, which makes
   // both exchange patterns of the pass (8 lanes x 4 rows at stride 8, and 8-word runs) hit 16 distinct bank pairs
   // (the i + i/32 padding left the stride-8 pattern 4-way conflicted: 8.7M conflicts per launch in profiles/r1_ntt_*).
@@ -48,7 +50,7 @@ struct FastTile {
     const int logstride = LOGP - t - NS;
 #pragma unroll
     for (int q = 0; q < (8 >> NS); q++) {
-      const u32 gid = threadIdx.x + q * 512;
+      const u32 gid = threadIdx.x + q * NT;
       u32 b, a_lo, a_hi;
       if (COLS) {
         b = gid & (B - 1);
@@ -195,7 +197,7 @@ struct FastTile {
                                                   const LimbDev& L) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const u32 i = k * 512 + threadIdx.x;   // consecutive lanes -> consecutive words: 256 B per request, no conflicts
+      const u32 i = k * NT + threadIdx.x;   // consecutive lanes -> consecutive words: 256 B per request, no conflicts
       u64 v = src[i];
       if (reduce_on_load) v = barrett64(v, L.p, L.bhi, L.blo);
       buf[phys(i)] = v;
@@ -204,7 +206,7 @@ struct FastTile {
   static __device__ __forceinline__ void stage_out(u64* __restrict__ dst, const u64* buf) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const u32 i = k * 512 + threadIdx.x;
+      const u32 i = k * NT + threadIdx.x;
       dst[i] = buf[phys(i)];
     }
   }
@@ -253,10 +255,10 @@ __device__ __forceinline__ void decode_block(const NttArgs& A, u32 tiles, u32& r
   tile = blockIdx.x % tiles;
 }
 
-template <int LOGP, bool COLS, bool INV>
-__global__ void __launch_bounds__(512, 2) ntt_fast_kernel(NttArgs A) {
+template <int LOGP, bool COLS, bool INV, int TLOG>
+__global__ void __launch_bounds__(1 << (TLOG - 3), 2 << (12 - TLOG)) ntt_fast_kernel(NttArgs A) {
   extern __shared__ u64 sm[];
-  constexpr int LOGB = 12 - LOGP;
+  constexpr int LOGB = TLOG - LOGP;
   u32 row, tile;
   const u64* src;
   u64* dst;
@@ -273,15 +275,15 @@ __global__ void __launch_bounds__(512, 2) ntt_fast_kernel(NttArgs A) {
   } else {
     const u32 tiles = (1u << A.logn1) >> LOGB;
     decode_block(A, tiles, row, tile);
-    src = A.in + ((size_t)(row / A.in_div) << A.logn) + ((size_t)tile << 12);
-    dst = A.out + ((size_t)row << A.logn) + ((size_t)tile << 12);
+    src = A.in + ((size_t)(row / A.in_div) << A.logn) + ((size_t)tile << TLOG);
+    dst = A.out + ((size_t)row << A.logn) + ((size_t)tile << TLOG);
     row0 = tile << LOGB;
     s_base = (int)A.logn1;
   }
   const LimbDev& L = A.limbs[A.ids[row % A.limbs_per_poly]];
   const bool first_pass = COLS || A.logn1 == 0;
   // (a lazy forward transform never meets the `stage == logn` test that selects the fully reducing last stage)
-  FastTile<LOGP, COLS, INV, false>::run(src, dst, gstride_a, sm, A.reduce_on_load != 0, L, s_base,
+  FastTile<LOGP, COLS, INV, false, TLOG>::run(src, dst, gstride_a, sm, A.reduce_on_load != 0, L, s_base,
                                         (!INV && A.lazy_out) ? 0xffu : A.logn, row0, first_pass);
 }
 

@@ -48,3 +48,31 @@ def gather_checksums(local: List[int], device=None) -> List[int]:
     for s, o in zip(sizes, out):
         res += [int(x) for x in o[: int(s.item())].cpu()]
     return res
+
+
+def bind_host_thread_to_gpu(device_index: int) -> str:
+    """Pin the calling host thread (and thereby the first-touch placement of the pinned staging buffers it allocates
+    next) to the CPUs of the NUMA node the GPU hangs off.  On two-socket boxes a staging buffer on the far socket
+    halves the PCIe rate of the end-to-end path.  Returns a short description of what was done; never raises."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        handle = None
+        uuid = getattr(props, "uuid", None)
+        if uuid is not None:
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                handle = None
+        if handle is None and hasattr(props, "pci_bus_id"):
+            bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        if handle is None:
+            return "no NVML handle"
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        import os
+        return "bound to %d CPUs of the GPU's NUMA node" % len(os.sched_getaffinity(0))
+    except Exception as e:  # noqa: BLE001 -- affinity is an optimisation, not a requirement
+        return "not bound (%s)" % type(e).__name__
