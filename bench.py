@@ -47,6 +47,15 @@ def ntt_traffic():
         return None
 
 
+def ntt_multiplier_pipe():
+    """busy fraction of the FMA-heavy pipe (where the integer multiplies run) of the same launches, same capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ntt_traffic.json")) as f:
+            return json.load(f).get("fmaheavy_busy_pct")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason sampling during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -356,7 +365,7 @@ def main():
         peak, how = peaks()
         roof = {"bound": "hbm", "kernel": "ntt_fast_kernel<8,1,*> (cols pass) + ntt_fast_kernel<6,0,*> (rows pass): one batched %d-row NTT, N=2^14" % rows,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
-                "traffic": ntt_traffic(), "ms_per_launch": ntt_ms,
+                "traffic": ntt_traffic(), "ms_per_launch": ntt_ms, "multiplier_pipe": ntt_multiplier_pipe(),
                 "note": "algorithmic bytes = 16*N per limb-NTT (SURVEY 8d). The transform is bound by the integer "
                         "multiplier pipe, not by HBM: see issue_roofline and DESIGN.md section 3",
                 # second roofline for the same launches: 62-bit Harvey/Shoup butterflies per second against the

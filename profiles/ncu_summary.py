@@ -11,7 +11,8 @@ dram__bytes_read.sum dram__bytes_write.sum gpu__dram_throughput.avg.pct_of_peak_
 lts__t_sector_hit_rate.pct l1tex__t_sector_hit_rate.pct lts__throughput.avg.pct_of_peak_sustained_elapsed
 smsp__issue_active.avg.pct_of_peak_sustained_active sm__inst_executed.avg.per_cycle_elapsed smsp__inst_executed.sum
 sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active
-sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active
+sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed
+sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active
 l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum
 l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum sm__cycles_elapsed.avg""".split()
 
