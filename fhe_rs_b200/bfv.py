@@ -23,6 +23,15 @@ __all__ = ["BfvParameters", "BfvParametersBuilder", "Ciphertext", "KeySwitchingK
            "GaloisKey", "EvaluationKey", "Multiplicator", "ScalingFactor", "dot_product_scalar", "FheError", "NTT", "POWER_BASIS"]
 
 
+def _release(free_name: str, handle) -> None:
+    """Call a C-ABI destructor from __del__; at interpreter shutdown the module globals may already be gone, in which
+    case the process is about to release everything anyway."""
+    try:
+        getattr(_capi.lib(), free_name)(handle)
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def _ptr(a: np.ndarray) -> int:
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data
@@ -72,7 +81,7 @@ class BfvParameters:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            _capi.lib().fhe_b200_params_destroy(h)
+            _release("fhe_b200_params_destroy", h)
 
     def degree(self) -> int:  # parameters.rs:130
         return self._degree
@@ -177,7 +186,7 @@ class Ciphertext:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            _capi.lib().fhe_b200_batch_free(h)
+            _release("fhe_b200_batch_free", h)
 
     # -- shape
     def _info(self):
@@ -362,7 +371,7 @@ class KeySwitchingKey:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            _capi.lib().fhe_b200_ksk_free(h)
+            _release("fhe_b200_ksk_free", h)
 
     def key_switch(self, p: Ciphertext, part: int = 0) -> Ciphertext:
         """KeySwitchingKey::key_switch (key_switching_key.rs:241-270) on polynomial `part` of a
@@ -597,10 +606,7 @@ class Multiplicator:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            try:
-                _capi.lib().fhe_b200_multiplicator_free(h)
-            except Exception:
-                pass
+            _release("fhe_b200_multiplicator_free", h)
 
     def enable_relinearization(self, rk: RelinearizationKey):  # mul.rs:141-151
         if rk.ksk.par is not self.par or rk.ksk.ciphertext_level != self.level:

@@ -71,10 +71,11 @@ struct DotArgs {
   const LimbDev* limbs;
   unsigned short ids[kMaxPos];
 };
-// out[g][part][limb][:] = sum_i ct[(g*n + i) % ct_count][part][limb][:] * pt[(g*n + i) % pt_count][limb][:]
+// out[g][part][limb][:] = sum_i ct[g*n + i][part][limb][:] * pt[g*n + i][limb][:]   (an operand with only n entries
+// is shared by all groups)
 // (bfv/ops/dot_product.rs:55-184: u128 fused multiply-adds per coefficient, one reduction at the end; the lazy
 // register here is 160 bits wide, so no term-count threshold / fallback path is needed).  HBM-bound: two words
-// read per multiply; two terms in flight per trip.
+// read per multiply; four terms in flight per trip.
 __global__ void dot_kernel(DotArgs A) {
   const u32 N = 1u << A.logn;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over groups*parts*limbs*N
@@ -91,15 +92,21 @@ __global__ void dot_kernel(DotArgs A) {
   const u64* pp = A.pt + ((size_t)limb << A.logn) + c;
   Acc192 acc;
   acc.clear();
-  const size_t i0 = (size_t)g * A.n_terms;
+  // an operand holds either n_terms entries (shared by every group) or groups * n_terms (checked by the caller)
+  cp += (A.ct_count == A.n_terms ? 0 : (size_t)g * A.n_terms) * ct_stride;
+  pp += (A.pt_count == A.n_terms ? 0 : (size_t)g * A.n_terms) * pt_stride;
   u32 i = 0;
-  for (; i + 2 <= A.n_terms; i += 2) {
-    const u64 x0 = cp[((i0 + i) % A.ct_count) * ct_stride], x1 = cp[((i0 + i + 1) % A.ct_count) * ct_stride];
-    const u64 y0 = pp[((i0 + i) % A.pt_count) * pt_stride], y1 = pp[((i0 + i + 1) % A.pt_count) * pt_stride];
-    acc.mac(x0, y0);
-    acc.mac(x1, y1);
+  for (; i + 4 <= A.n_terms; i += 4) {   // eight independent loads in flight
+    u64 x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      x[k] = cp[(size_t)(i + k) * ct_stride];
+      y[k] = pp[(size_t)(i + k) * pt_stride];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc.mac(x[k], y[k]);
   }
-  if (i < A.n_terms) acc.mac(cp[((i0 + i) % A.ct_count) * ct_stride], pp[((i0 + i) % A.pt_count) * pt_stride]);
+  for (; i < A.n_terms; i++) acc.mac(cp[(size_t)i * ct_stride], pp[(size_t)i * pt_stride]);
   A.out[idx] = acc.reduce(M);
 }
 
