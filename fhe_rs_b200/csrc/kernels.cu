@@ -487,54 +487,55 @@ struct KsMacArgs {
 // One thread per (limb j, ciphertext, coefficient), limb-major: consecutive CTAs work on the same key limb for
 // every ciphertext of the chunk, so the 2 x n_dig key rows of that limb (7 MB at set C) stay in L2 while the digit
 // rows stream through -- each key word leaves HBM once per chunk instead of once per ciphertext.
-template <int M>
-__global__ void ksmac_kernel(KsMacArgs A, u32 ct_begin, u32 n_groups) {
+__global__ void ksmac_kernel(KsMacArgs A) {
   const u32 N = 1u << A.logn;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over Lk*n_groups*N
-  size_t total = ((size_t)n_groups * A.Lk) << A.logn;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over Lk*cts*N
+  size_t total = ((size_t)A.cts * A.Lk) << A.logn;
   if (idx >= total) return;
-  const u32 c = idx & (N - 1);
+  u32 c = idx & (N - 1);
   size_t row = idx >> A.logn;
-  const u32 grp = row % n_groups, j = row / n_groups;
-  const u32 ct0 = ct_begin + grp * M;
-  const LimbDev& Md = A.limbs[A.ids[j]];
-  Acc192 a0[M], a1[M];
-#pragma unroll
-  for (int m = 0; m < M; m++) { a0[m].clear(); a1[m].clear(); }
-  const size_t dstride = (size_t)A.Lk << A.logn, cstride = (size_t)A.n_dig * dstride;
-  const u64* t_ptr = A.inter + ((((size_t)ct0 * A.n_dig) * A.Lk + j) << A.logn) + c;
+  u32 ct = row % A.cts, j = row / A.cts;
+  const LimbDev& M = A.limbs[A.ids[j]];
+  Acc192 a0, a1;
+  a0.clear();
+  a1.clear();
+  const u64* t_ptr = A.inter + ((((size_t)ct * A.n_dig) * A.Lk + j) << A.logn) + c;
   const u64* k0_ptr = A.k0 + ((size_t)j << A.logn) + c;
   const u64* k1_ptr = A.k1 + ((size_t)j << A.logn) + c;
-  // every key word fetched (from L2, see above) is multiplied with the digits of M ciphertexts; the words of the
-  // next digit are requested before the multiplies of the current one
-  u64 t[M], x = __ldg(k0_ptr), y = __ldg(k1_ptr);
-#pragma unroll
-  for (int m = 0; m < M; m++) t[m] = t_ptr[m * cstride];
-  for (u32 i = 0; i < A.n_dig; i++) {
-    u64 ct_[M];
-    const u64 cx = x, cy = y;
-#pragma unroll
-    for (int m = 0; m < M; m++) ct_[m] = t[m];
-    if (i + 1 < A.n_dig) {
-      x = __ldg(k0_ptr + (size_t)(i + 1) * dstride);
-      y = __ldg(k1_ptr + (size_t)(i + 1) * dstride);
-#pragma unroll
-      for (int m = 0; m < M; m++) t[m] = t_ptr[m * cstride + (size_t)(i + 1) * dstride];
-    }
-#pragma unroll
-    for (int m = 0; m < M; m++) {
-      a0[m].mac(ct_[m], cx);
-      a1[m].mac(ct_[m], cy);
-    }
+  const size_t dstride = (size_t)A.Lk << A.logn;
+  // two digits per trip, the six words of the next trip requested before the multiplies of this one (the kernel
+  // is bound by HBM latency, not by the multiplier: 2 x n_dig x 8 IMAD.WIDE per 48 bytes read).  Two
+  // coefficients per thread with 16-byte accesses, and four ciphertexts per thread sharing each key word (a third
+  // of the L2 -> SM bytes), both measured the same or slower: ~3.0 TB/s of HBM reads either way (profiles/microbench_r1.txt)
+  u32 i = 0;
+  u64 t0 = 0, t1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  if (A.n_dig >= 2) {
+    t0 = t_ptr[0], t1 = t_ptr[dstride];
+    x0 = __ldg(k0_ptr), x1 = __ldg(k0_ptr + dstride);
+    y0 = __ldg(k1_ptr), y1 = __ldg(k1_ptr + dstride);
   }
-#pragma unroll
-  for (int m = 0; m < M; m++) {
-    const size_t o = (((size_t)(ct0 + m) * A.out_ct_rows + j) << A.logn) + c;
-    if (A.base0) a0[m].add64(A.base0[o]);
-    if (A.base1) a1[m].add64(A.base1[o]);
-    A.out0[o] = a0[m].reduce(Md);
-    A.out1[o] = a1[m].reduce(Md);
+  for (; i + 2 <= A.n_dig; i += 2) {
+    const u64 ct0 = t0, ct1 = t1, cx0 = x0, cx1 = x1, cy0 = y0, cy1 = y1;
+    if (i + 4 <= A.n_dig) {
+      t0 = t_ptr[(size_t)(i + 2) * dstride], t1 = t_ptr[(size_t)(i + 3) * dstride];
+      x0 = __ldg(k0_ptr + (size_t)(i + 2) * dstride), x1 = __ldg(k0_ptr + (size_t)(i + 3) * dstride);
+      y0 = __ldg(k1_ptr + (size_t)(i + 2) * dstride), y1 = __ldg(k1_ptr + (size_t)(i + 3) * dstride);
+    }
+    a0.mac(ct0, cx0);
+    a1.mac(ct0, cy0);
+    a0.mac(ct1, cx1);
+    a1.mac(ct1, cy1);
   }
+  if (i < A.n_dig) {
+    const u64 tl = t_ptr[(size_t)i * dstride];
+    a0.mac(tl, __ldg(k0_ptr + (size_t)i * dstride));
+    a1.mac(tl, __ldg(k1_ptr + (size_t)i * dstride));
+  }
+  const size_t o = (((size_t)ct * A.out_ct_rows + j) << A.logn) + c;
+  if (A.base0) a0.add64(A.base0[o]);
+  if (A.base1) a1.add64(A.base1[o]);
+  A.out0[o] = a0.reduce(M);
+  A.out1[o] = a1.reduce(M);
 }
 
 // ------------------------------------------------------------------ gather / switch_down
@@ -730,17 +731,10 @@ void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* bas
   A.cts = cts; A.n_dig = n_dig; A.Lk = Lk; A.out_ct_rows = out_ct_rows; A.logn = logn;
   A.limbs = limbs;
   copy_ids(A.ids, ids);
-  const u32 g2 = cts / 2, rest = cts % 2;
-  if (g2) {
-    size_t total = ((size_t)g2 * Lk) << logn;
-    ksmac_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, 0, g2);
-    g_launches++;
-  }
-  if (rest) {
-    size_t total = ((size_t)rest * Lk) << logn;
-    ksmac_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, g2 * 2, rest);
-    g_launches++;
-  }
+  size_t total = ((size_t)cts * Lk) << logn;
+  if (!total) return;
+  ksmac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+  g_launches++;
 }
 
 void launch_gather(const u64* in, u64* out, size_t n_rows, const int* perm, u32 logn, cudaStream_t st) {
