@@ -51,6 +51,7 @@ SYMBOLS = {
     "fhe_b200_sub": (_i, [_vp, _vp, _vp]),
     "fhe_b200_neg": (_i, [_vp, _vp]),
     "fhe_b200_mul_plain": (_i, [_vp, _vp, _u32, _vp]),
+    "fhe_b200_add_plain": (_i, [_vp, _vp, _u32, _i, _vp]),
     "fhe_b200_dot_product_scalar": (_i, [_vp, _vp, _u32, _vp, _vp]),
     "fhe_b200_mul": (_i, [_vp, _vp, _vp, _vp]),
     "fhe_b200_relinearize": (_i, [_vp, _vp, _vp, _vp]),

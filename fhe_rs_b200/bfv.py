@@ -336,6 +336,29 @@ class Ciphertext:
         check(_capi.lib().fhe_b200_switch_down(self._h, self.stream))
         return self
 
+    def add_plain(self, poly: np.ndarray, subtract: bool = False) -> "Ciphertext":
+        """Ciphertext += &Plaintext / -= &Plaintext (ops/mod.rs:88-97, :188-197), in place: `poly` is the plaintext's
+        `to_poly()` words (delta-scaled, NTT), [limbs][N] shared by the batch or [count][limbs][N]."""
+        w = np.ascontiguousarray(poly, dtype=np.uint64)
+        n = 1 if w.ndim == 2 else w.shape[0]
+        check(_capi.lib().fhe_b200_add_plain(self._h, _ptr(w), n, 1 if subtract else 0, self.stream))
+        return self
+
+    def sub_plain(self, poly: np.ndarray) -> "Ciphertext":
+        return self.add_plain(poly, subtract=True)
+
+    def max_switchable_level(self) -> int:  # ciphertext.rs:187-189
+        return self.par.max_level()
+
+    def switch_to_level(self, target_level: int) -> "Ciphertext":
+        """Ciphertext::switch_to_level (ciphertext.rs:164-184): only moves down; InvalidLevel otherwise."""
+        if target_level < self.level or target_level > self.max_switchable_level():
+            raise FheError(_capi.INVALID_LEVEL, "InvalidLevel: level %d, min %d, max %d"
+                           % (target_level, self.level, self.max_switchable_level()))
+        while self.level < target_level:
+            self.switch_down()
+        return self
+
     def substitute(self, exponent: int) -> "Ciphertext":
         """Poly::substitute on every polynomial (rq/mod.rs:360-389)."""
         out = self._like()

@@ -783,10 +783,11 @@ int fhe_b200_add(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream) { ret
 int fhe_b200_sub(fhe_b200_batch* a, const fhe_b200_batch* b, void* stream) { return ew(EW_SUB, a, b, stream); }
 int fhe_b200_neg(fhe_b200_batch* a, void* stream) { return ew(EW_NEG, a, nullptr, stream); }
 
-int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, void* stream) {
+static int plain_op(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, u32 op, void* stream) {
   API_BEGIN
   REQUIRE(a && host_polys, FHE_B200_INVALID_ARGUMENT, "null argument");
   REQUIRE(n_polys == 1 || n_polys == a->count, FHE_B200_INVALID_ARGUMENT, "n_polys must be 1 or the batch size");
+  REQUIRE(a->parts >= 1, FHE_B200_BAD_POLY_COUNT, "empty ciphertext");
   need_repr(a, FHE_B200_NTT);
   const fhe_b200_params* par = a->par;
   DeviceGuard g(par);
@@ -795,10 +796,16 @@ int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n
   const size_t words = ((size_t)n_polys * a->limbs) << par->logn;
   u64* pt = ws.words(words);
   FHE_CUDA(cudaMemcpyAsync(pt, host_polys, words * sizeof(u64), cudaMemcpyHostToDevice, st));
-  launch_mul_plain(a->d, pt, a->count, a->parts, n_polys, ids_of(a), par->d_limbs, par->logn, st);
+  launch_mul_plain(a->d, pt, a->count, a->parts, n_polys, ids_of(a), par->d_limbs, par->logn, st, op);
   FHE_CUDA(cudaGetLastError());
   FHE_CUDA(cudaStreamSynchronize(st));   // host_polys may be pageable: do not return before it has been read
   API_END
+}
+int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, void* stream) {
+  return plain_op(a, host_polys, n_polys, 0, stream);
+}
+int fhe_b200_add_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, int subtract, void* stream) {
+  return plain_op(a, host_polys, n_polys, subtract ? 2 : 1, stream);
 }
 
 int fhe_b200_dot_product_scalar(const fhe_b200_batch* cts, const fhe_b200_batch* pts, uint32_t n_terms,

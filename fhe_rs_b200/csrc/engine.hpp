@@ -36,9 +36,10 @@ enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2 };
 void launch_ew(EwOp op, u64* a, const u64* b, size_t n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
                cudaStream_t st);
 
-// a[ct][part][limb][:] *= pt[ct % n_pt][limb][:]   (Modulus::mul_vec, zq/mod.rs:332)
+// op 0: a[ct][part][limb][:] *= pt[ct % n_pt][limb][:]   (Modulus::mul_vec, zq/mod.rs:332)
+// op 1 / 2: a[ct][0][limb][:] +=/-= pt[ct % n_pt][limb][:]   (Ciphertext +=/-= &Plaintext, ops/mod.rs:88-97, :188-197)
 void launch_mul_plain(u64* a, const u64* pt, u32 cts, u32 parts, u32 n_pt, const RowIds& ids, const LimbDev* limbs,
-                      u32 logn, cudaStream_t st);
+                      u32 logn, cudaStream_t st, u32 op = 0);
 
 // dot_product_scalar (bfv/ops/dot_product.rs:55-184): out[g] = sum_{i<n_terms} ct[(g*n+i) % ct_count] (.) pt[(g*n+i) % pt_count]
 // ct: [ct_count][parts][limbs][N], pt: [pt_count][limbs][N], out: [groups][parts][limbs][N], all NTT

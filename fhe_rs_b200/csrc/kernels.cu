@@ -47,6 +47,7 @@ struct MulPlainArgs {
   u64* a;
   const u64* pt;
   u32 cts, parts, n_pt, logn, limbs_per_poly;
+  u32 op;   // 0: every part *= pt (ops/mod.rs:229); 1: part 0 += pt (:88-97); 2: part 0 -= pt (:188-197)
   const LimbDev* limbs;
   unsigned short ids[kMaxPos];
 };
@@ -60,7 +61,12 @@ __global__ void mul_plain_kernel(MulPlainArgs A) {
   const u32 ct = (u32)(row / ((size_t)A.limbs_per_poly * A.parts));
   const LimbDev& M = A.limbs[A.ids[limb]];
   const u64 w = A.pt[((((size_t)(ct % A.n_pt)) * A.limbs_per_poly + limb) << A.logn) + c];
-  A.a[idx] = mulmod_limb(A.a[idx], w, M);
+  if (A.op == 0) {
+    A.a[idx] = mulmod_limb(A.a[idx], w, M);
+  } else if ((row / A.limbs_per_poly) % A.parts == 0) {
+    const u64 x = A.a[idx];
+    A.a[idx] = A.op == 1 ? csub(x + w, M.p) : csub(x + M.p - w, M.p);   // Modulus::add / sub, zq/mod.rs:103-128
+  }
 }
 
 // ------------------------------------------------------------------ dot_product_scalar
@@ -648,9 +654,9 @@ void launch_ew(EwOp op, u64* a, const u64* b, size_t n_rows, const RowIds& ids, 
 }
 
 void launch_mul_plain(u64* a, const u64* pt, u32 cts, u32 parts, u32 n_pt, const RowIds& ids, const LimbDev* limbs,
-                      u32 logn, cudaStream_t st) {
+                      u32 logn, cudaStream_t st, u32 op) {
   MulPlainArgs A;
-  A.a = a; A.pt = pt; A.cts = cts; A.parts = parts; A.n_pt = n_pt; A.logn = logn;
+  A.a = a; A.pt = pt; A.cts = cts; A.parts = parts; A.n_pt = n_pt; A.logn = logn; A.op = op;
   A.limbs_per_poly = ids.limbs_per_poly; A.limbs = limbs;
   copy_ids(A.ids, ids);
   size_t total = ((size_t)cts * parts * ids.limbs_per_poly) << logn;

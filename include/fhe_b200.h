@@ -136,6 +136,10 @@ int fhe_b200_neg(fhe_b200_batch* a, void* stream);
  * ciphertext is multiplied coefficient-wise by an NTT-domain polynomial.  host_polys holds n_polys polynomials of
  * [limbs][N] words (Plaintext::poly_ntt, or a monomial of EvaluationKey::expands); n_polys is 1 (shared) or count. */
 int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, void* stream);
+/* Ciphertext += &Plaintext / -= &Plaintext (bfv/ops/mod.rs:88-97, :188-197): part 0 of every ciphertext gets
+ * +/- Plaintext::to_poly() (the delta-scaled NTT polynomial the host computes, plaintext.rs:172-197); host_polys as for
+ * fhe_b200_mul_plain. */
+int fhe_b200_add_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, int subtract, void* stream);
 /* dot_product_scalar (bfv/ops/dot_product.rs:55-184): out[g] = sum_{i < n_terms} cts[g*n_terms + i] (.) pts[g*n_terms + i]
  * for g < out.count.  pts is a batch with one NTT polynomial per entry (Plaintext::poly_ntt); either operand may hold
  * n_terms entries only, shared by every group (the PIR loops of examples/mulpir.rs:153-181 share the expanded query

@@ -140,6 +140,11 @@ class Ciphertext {
     check(fhe_b200_mul(h_, rhs.h_, out.h_, stream_));
     return out;
   }
+  // Ciphertext += / -= &Plaintext (bfv/ops/mod.rs:88, :188): poly = Plaintext::to_poly() words, [limbs][N]
+  Ciphertext& add_plain(const std::vector<uint64_t>& poly, bool subtract = false) {
+    check(fhe_b200_add_plain(h_, poly.data(), 1, subtract ? 1 : 0, stream_));
+    return *this;
+  }
   // Ciphertext *= &Plaintext (bfv/ops/mod.rs:229): poly_ntt = [limbs][N] words shared by the batch
   Ciphertext& mul_plain(const std::vector<uint64_t>& poly_ntt) {
     check(fhe_b200_mul_plain(h_, poly_ntt.data(), 1, stream_));
@@ -147,6 +152,12 @@ class Ciphertext {
   }
   // Ciphertext::switch_down (bfv/ciphertext.rs:148)
   void switch_down() { check(fhe_b200_switch_down(h_, stream_)); }
+  // Ciphertext::switch_to_level (ciphertext.rs:164-184): only moves down
+  void switch_to_level(uint32_t target_level) {
+    if (target_level < level() || target_level > par_->max_level())
+      throw Error(FHE_B200_INVALID_LEVEL, "InvalidLevel");
+    while (level() < target_level) switch_down();
+  }
   // Rq.coefficients of every polynomial (rq/convert.rs:17-44): count*parts blobs of packed_bytes() each
   size_t packed_bytes() const {
     size_t n = 0;

@@ -899,6 +899,13 @@ class Ciphertext:
         self.level += 1
         return self
 
+    def switch_to_level(self, target_level: int):  # ciphertext.rs:164-184
+        if target_level < self.level or target_level > self.par.max_level():
+            raise ValueError("InvalidLevel")
+        while self.level < target_level:
+            self.switch_down()
+        return self
+
 
 class SecretKey:
     """keys/secret_key.rs (client side; oracle-only test plumbing)."""

@@ -347,6 +347,18 @@ def test_switch_down(oracle, F):
     with pytest.raises(F.FheError) as e:
         X.switch_down()
     assert e.value.code == -9
+    # Ciphertext::switch_to_level (ciphertext.rs:164-184)
+    Y = F.Ciphertext.from_host(gpar, x)
+    assert Y.max_switchable_level() == 3
+    Y.switch_to_level(2)
+    assert Y.level == 2 and Y.limbs == 2
+    got = Y.to_host()
+    for i in range(3):
+        assert (got[i] == oracle.Ciphertext.from_array(opar, x[i], 0).switch_to_level(2).to_array()).all()
+    for bad in (1, 4):   # moving up, or past the last level
+        with pytest.raises(F.FheError) as e:
+            Y.switch_to_level(bad)
+        assert e.value.code == -6
 
 
 def test_mixed_modulus_sizes(oracle, F):
@@ -569,6 +581,19 @@ def test_mul_plain_inner_sum_expand(oracle, F):
     for i in range(2):
         w = oracle.Poly(opar.context_at_level(0), oracle.NTT, per_ct[i])
         assert (got[i] == np.stack([p.mul(w).c for p in octs[i].c])).all()
+    # ct + pt, ct - pt (ops/mod.rs:88-97, :188-197): part 0 +/- Plaintext::to_poly(); decrypts to the slot-wise sum
+    pv = rng.integers(0, t, degree)
+    dp = oracle.plaintext_to_poly(opar, oracle.simd_encode(opar, pv), 0)
+    got_add = X.clone().add_plain(dp.c).to_host()
+    got_sub = X.clone().sub_plain(dp.c).to_host()
+    for i in range(2):
+        ea = octs[i].copy(); ea.c[0] = ea.c[0].copy().iadd(dp)
+        es = octs[i].copy(); es.c[0] = es.c[0].copy().isub(dp)
+        assert (got_add[i] == ea.to_array()).all() and (got_sub[i] == es.to_array()).all()
+        dec = oracle.simd_decode(opar, sk.decrypt(oracle.Ciphertext.from_array(opar, got_add[i], 0)))
+        assert (dec.astype(np.int64) == (vals[i] + pv) % t).all()
+        dec = oracle.simd_decode(opar, sk.decrypt(oracle.Ciphertext.from_array(opar, got_sub[i], 0)))
+        assert (dec.astype(np.int64) == (vals[i] - pv) % t).all()
     # inner sum
     ek = F.EvaluationKey(gpar)
     for e in exps:
