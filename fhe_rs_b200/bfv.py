@@ -396,8 +396,12 @@ class KeySwitchingKey:
         if h:
             _release("fhe_b200_ksk_free", h)
 
+    @staticmethod
+    def from_arrays(par: BfvParameters, c0, c1, ciphertext_level: int = 0, key_level: int = 0) -> "KeySwitchingKey":
+        return KeySwitchingKey(par, c0, c1, ciphertext_level, key_level)
+
     def key_switch(self, p: Ciphertext, part: int = 0) -> Ciphertext:
-        """KeySwitchingKey::key_switch (key_switching_key.rs:241-270) on polynomial `part` of a
+        """KeySwitchingKey::key_switch (key_switching_key.rs:241-270, :323-362) on polynomial `part` of a
         POWER_BASIS batch; returns the (c0, c1) pair as a 2-part NTT batch at the key level."""
         out = Ciphertext(self.par, p.count, 2, self.ksk_level, NTT, p.stream)
         check(_capi.lib().fhe_b200_key_switch(p._h, part, self._h, out._h, p.stream))

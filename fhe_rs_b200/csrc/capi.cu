@@ -177,6 +177,7 @@ struct fhe_b200_batch {
 struct fhe_b200_ksk {
   const fhe_b200_params* par;
   u32 ct_level, ksk_level, n_dig, Lk;
+  u32 log_base;   // 0: RNS-digit variant; else base-2^log_base decomposition (single-modulus key level)
   u64 *k0, *k1;
 };
 
@@ -331,6 +332,13 @@ void key_switch_core(const fhe_b200_params* par, const fhe_b200_ksk* k, const u6
   const LevelData& kl = par->level(k->ksk_level);
   const u32 L = k->n_dig, Lk = k->Lk;
   u64* inter = ws.words(((size_t)cts * L * Lk) << par->logn);
+  if (k->log_base) {
+    // key_switch_decomposition (key_switching_key.rs:323-362): the digits of the single residue, each below
+    // 2^log_base < q, transformed lazily like the RNS digits
+    u64* dig = ws.words(((size_t)cts * L) << par->logn);
+    launch_decompose(c2, dig, cts, L, k->log_base, par->logn, st);
+    launch_ntt(dig, inter, cts * L, kl.ctx_ids, par->d_limbs, par->logn, false, 1, false, st, true);
+  } else {
   // digit broadcast (rq/mod.rs:563-586), then NTT of every (digit, limb) row.  The reference lazily reduces the
   // digit modulo q_j before its lazy transform; the forward butterflies accept any input below 4*q_j, so the
   // reduction on load is only needed when a digit (< max q_i) can reach 4 * min q_j (mixed modulus sizes).
@@ -341,6 +349,7 @@ void key_switch_core(const fhe_b200_params* par, const fhe_b200_ksk* k, const u6
   // forward_vt_lazy (rq/mod.rs:580): the digits stay in [0,4q_j); the lazy accumulator of the inner product takes
   // any 64-bit operand and reduces once
   launch_ntt(c2, inter, cts * L * Lk, kl.ctx_ids, par->d_limbs, par->logn, false, Lk, reduce, st, true);
+  }
   launch_ksmac(inter, k->k0, k->k1, base0, base1, out0, out1, cts, L, Lk, out_ct_rows, kl.ctx_ids, par->d_limbs,
                par->logn, st);
 }
@@ -725,10 +734,22 @@ int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uin
   const LevelData& cl = p->level(ciphertext_level);
   const LevelData& kl = p->level(ksk_level);
   REQUIRE(ksk_level <= ciphertext_level, FHE_B200_INVALID_LEVEL, "key level must not exceed the ciphertext level");
-  REQUIRE(kl.L >= 2, FHE_B200_UNSUPPORTED, "single-modulus key level uses digit decomposition (not accelerated)");
-  REQUIRE(n_digits == cl.L, FHE_B200_CONTEXT_MISMATCH, "n_digits must equal the ciphertext level's limb count");
+  u32 log_base = 0;
+  if (kl.L == 1) {
+    // KeySwitchingKey::new (key_switching_key.rs:92-97): base-2^(log_modulus/2) decomposition of the single residue
+    REQUIRE(cl.L == 1, FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch: a single-modulus key serves the last level only");
+    const u64 q = p->moduli[0];
+    const u32 log_modulus = 64 - (u32)clz64(q - 1);   // next_power_of_two().ilog2()
+    log_base = log_modulus / 2;
+    REQUIRE(log_base >= 1, FHE_B200_UNSUPPORTED, "modulus too small for the decomposition");
+    REQUIRE(n_digits == (log_modulus + log_base - 1) / log_base, FHE_B200_CONTEXT_MISMATCH,
+            "n_digits must be ceil(log_modulus / log_base) for a single-modulus key");
+  } else {
+    REQUIRE(n_digits == cl.L, FHE_B200_CONTEXT_MISMATCH, "n_digits must equal the ciphertext level's limb count");
+  }
   std::unique_ptr<fhe_b200_ksk> k(new fhe_b200_ksk());
   k->par = p; k->ct_level = ciphertext_level; k->ksk_level = ksk_level; k->n_dig = n_digits; k->Lk = kl.L;
+  k->log_base = log_base;
   size_t bytes = ((size_t)n_digits * kl.L << p->logn) * sizeof(u64);
   k->k0 = k->k1 = nullptr;
   FHE_CUDA(cudaMalloc(&k->k0, bytes));

@@ -86,6 +86,10 @@ void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* bas
                   u64* out1, u32 cts, u32 n_dig, u32 Lk, u32 out_ct_rows, const RowIds& ids, const LimbDev* limbs,
                   u32 logn, cudaStream_t st);
 
+// base-2^log_base digit decomposition of single-limb polynomials (key_switching_key.rs:339-345):
+// in [polys][N] -> out [polys][n_dig][N]
+void launch_decompose(const u64* in, u64* out, size_t polys, u32 n_dig, u32 log_base, u32 logn, cudaStream_t st);
+
 // NTT-domain substitution gather (rq/mod.rs:368-377): out[row][t] = in[row][perm[t]]
 void launch_gather(const u64* in, u64* out, size_t n_rows, const int* perm, u32 logn, cudaStream_t st);
 

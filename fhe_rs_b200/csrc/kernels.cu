@@ -544,6 +544,21 @@ __global__ void ksmac_kernel(KsMacArgs A) {
   A.out1[o] = a1.reduce(M);
 }
 
+// base-2^log_base digits of a single-limb power-basis polynomial (key_switching_key.rs:339-345):
+// out[poly][d][:] = (in[poly][:] >> (d * log_base)) & (2^log_base - 1)
+__global__ void decompose_kernel(const u64* in, u64* out, size_t n_words, u32 n_dig, u32 log_base, u32 logn) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_words) return;
+  const size_t poly = i >> logn;
+  const u32 c = i & ((1u << logn) - 1);
+  u64 v = in[i];
+  const u64 mask = (1ull << log_base) - 1;
+  for (u32 d = 0; d < n_dig; d++) {
+    out[((poly * n_dig + d) << logn) + c] = v & mask;
+    v >>= log_base;
+  }
+}
+
 // ------------------------------------------------------------------ gather / switch_down
 __global__ void gather_kernel(const u64* in, u64* out, size_t n_words, const int* perm, u32 logn) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -740,6 +755,13 @@ void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* bas
   size_t total = ((size_t)cts * Lk) << logn;
   if (!total) return;
   ksmac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+  g_launches++;
+}
+
+void launch_decompose(const u64* in, u64* out, size_t polys, u32 n_dig, u32 log_base, u32 logn, cudaStream_t st) {
+  const size_t n_words = polys << logn;
+  if (!n_words) return;
+  decompose_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(in, out, n_words, n_dig, log_base, logn);
   g_launches++;
 }
 

@@ -117,8 +117,11 @@ int fhe_b200_batch_device_ptr(const fhe_b200_batch* b, uint64_t** dptr, size_t* 
 /* ---- keys -----------------------------------------------------------------------------
  * KeySwitchingKey (key_switching_key.rs:22-45): c0, c1 are the NTT-domain values of the
  * n_digits key polynomials at the key level, host layout [digit][limb][coeff];
- * n_digits must equal the limb count of ciphertext_level (:113).  Shoup companions
- * (Poly<NttShoup>) are not needed by the device inner product. */
+ * n_digits must equal the limb count of ciphertext_level (:113) -- or, when the key level has a
+ * single modulus q, ceil(log_modulus / log_base) with log_modulus = ilog2(next_power_of_two(q)),
+ * log_base = log_modulus / 2: the base-2^log_base decomposition variant (:92-110), whose key switch
+ * (key_switch_decomposition, :323-362) the library then runs.  Shoup companions (Poly<NttShoup>) are
+ * not needed by the device inner product. */
 int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uint32_t ksk_level,
                         const uint64_t* c0, const uint64_t* c1, uint32_t n_digits, fhe_b200_ksk** out);
 int fhe_b200_ksk_free(fhe_b200_ksk* k);

@@ -990,8 +990,19 @@ def simd_decode(par: BfvParameters, coeffs: np.ndarray) -> np.ndarray:
     return w[np.array(par.matrix_reps_index_map)]
 
 
+def _ksk_log_base(ctx_ksk: "Context"):
+    """key_switching_key.rs:92-97: a single-modulus key level decomposes in base 2^(log_modulus / 2);
+    returns (log_base, n_digits), (0, 0) for the RNS-digit variant."""
+    if len(ctx_ksk.moduli) != 1:
+        return 0, 0
+    log_modulus = (ctx_ksk.moduli[0] - 1).bit_length()      # next_power_of_two().ilog2()
+    log_base = log_modulus // 2
+    return log_base, -(-log_modulus // log_base)
+
+
 class KeySwitchingKey:
-    """keys/key_switching_key.rs:22-362 (RNS-digit variant; log_base == 0)."""
+    """keys/key_switching_key.rs:22-362: RNS-digit variant (log_base == 0) and, when the key level has a single
+    modulus, the base-2^log_base decomposition variant (:92-110, :196-236, :323-362)."""
 
     def __init__(self, sk: SecretKey, frm: Poly, ciphertext_level: int, ksk_level: int, rng):
         par = sk.par
@@ -1000,20 +1011,19 @@ class KeySwitchingKey:
         self.ctx_ciphertext = par.context_at_level(ciphertext_level)
         self.ciphertext_level, self.ksk_level = ciphertext_level, ksk_level
         assert frm.ctx == self.ctx_ksk and frm.rep == POWER_BASIS
-        if len(self.ctx_ksk.moduli) == 1:
-            raise NotImplementedError("single-modulus digit decomposition (:92-110) not in scope")
-        size = len(self.ctx_ciphertext.moduli)
+        self.log_base, n_dec = _ksk_log_base(self.ctx_ksk)
+        size = n_dec if self.log_base else len(self.ctx_ciphertext.moduli)
         # generate_c1 (:130-146): uniform NttShoup polys (numpy RNG instead of seeded ChaCha8)
         self.c1 = [Poly.random(self.ctx_ksk, NTT_SHOUP, rng) for _ in range(size)]
-        # generate_c0 (:149-194)
+        # generate_c0 (:149-194) / generate_c0_decomposition (:196-236)
         s = sk.s_ntt(self.ctx_ksk)
-        rns = RnsContext(par.moduli[:size])
+        rns = None if self.log_base else RnsContext(par.moduli[:size])
         self.c0 = []
         for i, c1i in enumerate(self.c1):
             a_s = Poly(self.ctx_ksk, NTT, c1i.c.copy()).imul(s).into_power_basis()
             b = Poly.from_i64(self.ctx_ksk, sample_vec_cbd(par.degree, par.variance, rng))
             b.isub(a_s)
-            b.iadd(frm.mul_scalar_big(rns.garner[i]))
+            b.iadd(frm.mul_scalar_big(1 << (i * self.log_base) if self.log_base else rns.garner[i]))
             self.c0.append(b.into_ntt_shoup())
 
     @staticmethod
@@ -1026,16 +1036,27 @@ class KeySwitchingKey:
         k.ctx_ksk = par.context_at_level(ksk_level)
         k.ctx_ciphertext = par.context_at_level(ciphertext_level)
         k.ciphertext_level, k.ksk_level = ciphertext_level, ksk_level
+        k.log_base, n_dec = _ksk_log_base(k.ctx_ksk)
+        assert len(c0) == len(c1) == (n_dec if k.log_base else len(k.ctx_ciphertext.moduli))
         k.c0 = [Poly(k.ctx_ksk, NTT_SHOUP, a) for a in c0]
         k.c1 = [Poly(k.ctx_ksk, NTT_SHOUP, a) for a in c1]
         return k
 
-    def key_switch(self, p: Poly):  # :241-270
+    def key_switch(self, p: Poly):  # :241-270, :323-362
         assert p.ctx == self.ctx_ciphertext and p.rep == POWER_BASIS
         c0 = Poly(self.ctx_ksk, NTT)
         c1 = Poly(self.ctx_ksk, NTT)
-        for i in range(len(self.c0)):
-            c2_i = lazy_constant_ntt(p.c[i], self.ctx_ksk)
+        if self.log_base:
+            coeffs = p.c[0].copy()
+            mask = np.uint64((1 << self.log_base) - 1)
+            digits = []
+            for _ in range(len(self.c0)):
+                digits.append(coeffs & mask)
+                coeffs = coeffs >> np.uint64(self.log_base)
+        else:
+            digits = [p.c[i] for i in range(len(self.c0))]
+        for i, d in enumerate(digits):
+            c2_i = lazy_constant_ntt(d, self.ctx_ksk)
             c0.iadd(c2_i.mul(self.c0[i]))
             c2_i.imul(self.c1[i])
             c1.iadd(c2_i)

@@ -561,6 +561,45 @@ def test_dot_product_scalar(oracle, F, degree, nmod, n_terms, groups):
         assert e.value.code == -6
 
 
+@pytest.mark.parametrize("degree,sizes", [(16, [62, 62, 62]), (64, [62, 50]), (4096, [62])])
+def test_single_modulus_key_switch(oracle, F, degree, sizes):
+    """KeySwitchingKey at a level with one modulus (key_switching_key.rs:92-110): base-2^(log q / 2) decomposition,
+    key_switch_decomposition (:323-362); and the RGSW external product at that level (rgsw_ciphertext.rs:122-155)."""
+    t = 1153
+    opar = oracle.BfvParameters(degree, t, moduli_sizes=sizes)
+    gpar = F.BfvParameters(degree, t, moduli=opar.moduli, device=0)
+    rng = np.random.default_rng(5 + degree)
+    last = len(sizes) - 1
+    ctx = opar.context_at_level(last)
+    sk = oracle.SecretKey(opar, rng)
+    frm = oracle.Poly.random(ctx, oracle.POWER_BASIS, rng)
+    ok = oracle.KeySwitchingKey(sk, frm, last, last, rng)
+    assert ok.log_base > 0 and len(ok.c0) in (2, 3)
+    gk = F.KeySwitchingKey.from_arrays(gpar, *ok.arrays(), ciphertext_level=last, key_level=last)
+    x = rand_ct(oracle, opar, rng, 3, 2, level=last)
+    X = F.Ciphertext.from_host(gpar, x, level=last, repr=F.POWER_BASIS)
+    for part in (0, 1):
+        got = gk.key_switch(X, part).to_host()
+        for i in range(3):
+            c0, c1 = ok.key_switch(oracle.Poly(ctx, oracle.POWER_BASIS, x[i, part].copy()))
+            assert (got[i, 0] == c0.c).all() and (got[i, 1] == c1.c).all()
+    # wrong digit count / a single-modulus key for a ciphertext level with more limbs
+    with pytest.raises(F.FheError) as e:
+        F.KeySwitchingKey.from_arrays(gpar, ok.arrays()[0][:1], ok.arrays()[1][:1], ciphertext_level=last, key_level=last)
+    assert e.value.code == -5
+    if degree <= 64:   # RGSW external product at the last level decrypts to the product (rgsw_ciphertext.rs tests)
+        m1, m2 = rng.integers(0, t, degree), rng.integers(0, t, degree)
+        ct = sk.encrypt(oracle.simd_encode(opar, m1), last, rng)
+        m2_ntt = oracle.Poly.from_u64(ctx, oracle.simd_encode(opar, m2), oracle.NTT)
+        org = oracle.RGSWCiphertext(sk, m2_ntt, last, rng)
+        grg = F.RGSWCiphertext.from_arrays(gpar, *org.ksk0.arrays(), *org.ksk1.arrays(), level=last)
+        CT = F.Ciphertext.from_host(gpar, ct.to_array()[None], level=last)
+        got = grg.external_product(CT).to_host()[0]
+        assert (got == org.external_product(ct).to_array()).all()
+        dec = oracle.simd_decode(opar, sk.decrypt(oracle.Ciphertext.from_array(opar, got, last)))
+        assert (dec.astype(np.int64) == (m1 * m2) % t).all()
+
+
 def test_mul_plain_inner_sum_expand(oracle, F):
     """Ciphertext * Plaintext (ops/mod.rs:229-238), EvaluationKey::computes_inner_sum (evaluation_key.rs:56-100)
     and EvaluationKey::expands (:192-256) -- the PIR examples' loops, built from the same kernels"""

@@ -356,6 +356,27 @@ def test_key_switch_noise_and_galois(oracle):
     assert (got == np.concatenate([v[row:], v[:row]])).all()
 
 
+def test_key_switch_decomposition(oracle):
+    """keys/key_switching_key.rs:595-627 `key_switch_decomposition`: a key at a single-modulus level (6 moduli, level
+    5) uses the base-2^(log q / 2) decomposition; c0 + c1*s - input*p stays below (bits(q) / 2) + 10 bits."""
+    rng = np.random.default_rng(595)
+    par = oracle.BfvParameters(16, 1153, moduli_sizes=[62] * 6)
+    ctx = par.context_at_level(5)
+    q = ctx.moduli[0]
+    for _ in range(10):
+        sk = oracle.SecretKey(par, rng)
+        p = oracle.Poly.from_i64(ctx, oracle.sample_vec_cbd(16, 10, rng))
+        ksk = oracle.KeySwitchingKey(sk, p, 5, 5, rng)
+        assert ksk.log_base == 31 and len(ksk.c0) == 2
+        inp = oracle.Poly.random(ctx, oracle.POWER_BASIS, rng)
+        c0, c1 = ksk.key_switch(inp)
+        c2 = c0.copy().iadd(c1.copy().imul(sk.s_ntt(ctx))).into_power_basis()
+        c3 = inp.copy().into_ntt().imul(p.copy().into_ntt()).into_power_basis()
+        for a, b in zip(c2.c[0], c3.c[0]):
+            d = (int(a) - int(b)) % q
+            assert min(d.bit_length(), (q - d).bit_length()) <= q.bit_length() // 2 + 10
+
+
 def test_leveled_keys(oracle):
     """relinearization_key.rs:226-290: ciphertext at level 1, key at level 0 (switch down after key switch)"""
     rng = np.random.default_rng(31)
