@@ -34,6 +34,32 @@ struct LevelData {
   SwitchDownDev sd;
 };
 
+// Device copy of one RnsScaler's tables (rns/scaler.rs:79-175).  `to_dev` uploads a vector and keeps ownership of the
+// allocation, `index_of` maps a modulus of the `to` basis to its slot in the limb table the kernels will be given.
+template <typename ToDev, typename IndexOf>
+void upload_scaler_tables(ScalerData& s, const std::vector<u64>& to_moduli, ToDev&& to_dev, IndexOf&& index_of) {
+  ScalerDev& d = s.dev;
+  std::memset(&d, 0, sizeof(d));
+  d.n_from = s.h.n_from; d.n_to = s.h.n_to; d.is_one = s.h.is_one; d.shift = s.h.shift;
+  d.tg_lo = s.h.theta_gamma_lo; d.tg_hi = s.h.theta_gamma_hi; d.tg_sign = s.h.theta_gamma_sign;
+  for (size_t j = 0; j < to_moduli.size(); j++) d.to_ids[j] = (unsigned short)index_of(to_moduli[j]);
+  d.gamma = to_dev(s.h.gamma);
+  d.omega = to_dev(s.h.omega);
+  d.to_lo = to_dev(s.h.theta_omega_lo);
+  d.to_hi = to_dev(s.h.theta_omega_hi);
+  d.to_sign = to_dev(s.h.theta_omega_sign);
+  // source indices of the theta_omega terms, positive sign first (the kernel makes one pass per sign)
+  std::vector<unsigned char> order;
+  for (int sg = 0; sg < 2; sg++)
+    for (size_t i = 0; i < s.h.theta_omega_sign.size(); i++)
+      if ((int)s.h.theta_omega_sign[i] == sg) order.push_back((unsigned char)i);
+  d.n_pos = 0;
+  for (unsigned char v : s.h.theta_omega_sign) d.n_pos += v == 0;
+  d.to_order = to_dev(order);
+  d.tgar_lo = to_dev(s.h.theta_garner_lo);
+  d.tgar_hi = to_dev(s.h.theta_garner_hi);
+}
+
 }  // namespace
 
 struct fhe_b200_params {
@@ -69,27 +95,7 @@ struct fhe_b200_params {
     return -1;
   }
   void upload_scaler(ScalerData& s, const std::vector<u64>& to_moduli) const {
-    ScalerDev& d = s.dev;
-    std::memset(&d, 0, sizeof(d));
-    d.n_from = s.h.n_from; d.n_to = s.h.n_to; d.is_one = s.h.is_one; d.shift = s.h.shift;
-    d.tg_lo = s.h.theta_gamma_lo; d.tg_hi = s.h.theta_gamma_hi; d.tg_sign = s.h.theta_gamma_sign;
-    for (size_t j = 0; j < to_moduli.size(); j++) d.to_ids[j] = (unsigned short)prime_index(to_moduli[j]);
-    d.gamma = to_dev(s.h.gamma);
-    d.omega = to_dev(s.h.omega);
-    d.to_lo = to_dev(s.h.theta_omega_lo);
-    d.to_hi = to_dev(s.h.theta_omega_hi);
-    d.to_sign = to_dev(s.h.theta_omega_sign);
-    {
-      std::vector<unsigned char> order;
-      for (int sg = 0; sg < 2; sg++)
-        for (size_t i = 0; i < s.h.theta_omega_sign.size(); i++)
-          if ((int)s.h.theta_omega_sign[i] == sg) order.push_back((unsigned char)i);
-      d.n_pos = 0;
-      for (unsigned char v : s.h.theta_omega_sign) d.n_pos += v == 0;
-      d.to_order = to_dev(order);
-    }
-    d.tgar_lo = to_dev(s.h.theta_garner_lo);
-    d.tgar_hi = to_dev(s.h.theta_garner_hi);
+    upload_scaler_tables(s, to_moduli, [&](const auto& v) { return to_dev(v); }, [&](u64 q) { return prime_index(q); });
   }
 
   // ContextLevel + MultiplicationParameters of one level (bfv/parameters.rs:600-700, :793-813)
@@ -207,27 +213,7 @@ struct fhe_b200_multiplicator {
     return -1;
   }
   void upload_scaler(ScalerData& sd, const std::vector<u64>& to_moduli) {
-    ScalerDev& d = sd.dev;
-    std::memset(&d, 0, sizeof(d));
-    d.n_from = sd.h.n_from; d.n_to = sd.h.n_to; d.is_one = sd.h.is_one; d.shift = sd.h.shift;
-    d.tg_lo = sd.h.theta_gamma_lo; d.tg_hi = sd.h.theta_gamma_hi; d.tg_sign = sd.h.theta_gamma_sign;
-    for (size_t j = 0; j < to_moduli.size(); j++) d.to_ids[j] = (unsigned short)prime_index(to_moduli[j]);
-    d.gamma = to_dev(sd.h.gamma);
-    d.omega = to_dev(sd.h.omega);
-    d.to_lo = to_dev(sd.h.theta_omega_lo);
-    d.to_hi = to_dev(sd.h.theta_omega_hi);
-    d.to_sign = to_dev(sd.h.theta_omega_sign);
-    {
-      std::vector<unsigned char> order;
-      for (int sg = 0; sg < 2; sg++)
-        for (size_t i = 0; i < sd.h.theta_omega_sign.size(); i++)
-          if ((int)sd.h.theta_omega_sign[i] == sg) order.push_back((unsigned char)i);
-      d.n_pos = 0;
-      for (unsigned char v : sd.h.theta_omega_sign) d.n_pos += v == 0;
-      d.to_order = to_dev(order);
-    }
-    d.tgar_lo = to_dev(sd.h.theta_garner_lo);
-    d.tgar_hi = to_dev(sd.h.theta_garner_hi);
+    upload_scaler_tables(sd, to_moduli, [&](const auto& v) { return to_dev(v); }, [&](u64 q) { return prime_index(q); });
   }
 };
 
