@@ -30,6 +30,27 @@ def test_library_exports_every_declared_symbol(F):
     assert b"sm_100a" in lib.fhe_b200_version()
 
 
+def test_ctypes_signatures_match_the_header(F):
+    """the hand-written ctypes table must agree with the prototypes of include/fhe_b200.h: argument count, and
+    pointer-vs-integer kind of every argument (a mismatch corrupts the call silently)"""
+    import ctypes as C
+    from fhe_rs_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "fhe_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b[a-z_0-9]+\s*\*?\s*(fhe_b200_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", hdr)
+    assert len(protos) == len(_capi.SYMBOLS)
+    for name, args in protos:
+        params = [a.strip() for a in args.split(",")]
+        if params == ["void"]:
+            params = []
+        restype, argtypes = _capi.SYMBOLS[name]
+        assert len(params) == len(argtypes), (name, params, argtypes)
+        for decl, ct in zip(params, argtypes):
+            is_ptr = "*" in decl
+            ct_ptr = ct in (C.c_void_p, C.c_char_p) or hasattr(ct, "contents") or getattr(ct, "_type_", None) == "P"
+            assert is_ptr == bool(ct_ptr), (name, decl, ct)
+
+
 def test_cubin_is_sm_100a(F):
     import subprocess
     from fhe_rs_b200 import _capi
