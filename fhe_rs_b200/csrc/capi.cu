@@ -291,7 +291,7 @@ struct Workspace {
 u32 chunk_size() {
   static u32 c = [] {
     const char* e = getenv("FHE_B200_CHUNK");
-    int v = e ? atoi(e) : 64;
+    int v = e ? atoi(e) : 128;   // ~15 GB of scratch per in-flight chunk at set C; fewer kernel tails than 64 (+0.5%)
     return (u32)(v < 1 ? 1 : v);
   }();
   return c;
