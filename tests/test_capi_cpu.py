@@ -150,3 +150,41 @@ def test_golden_fixture_matches_oracle(oracle):
             k, v = i + j, int(ma[i]) * int(mb[j])
             exp[k % 16] = (exp[k % 16] + (v if k < 16 else -v)) % 1153
     assert (sk.decrypt(res).astype(object) == exp).all()
+
+
+def test_wide_golden_fixture_matches_oracle(oracle):
+    """tests/golden/golden_n16_l3_wide.npz (operations around the core): the oracle reproduces the stored outputs
+    from the stored inputs, and the stored results decrypt to what the operations mean"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_n16_l3_wide.npz"))
+    t, degree = int(g["t"]), int(g["degree"])
+    par = oracle.BfvParameters(degree, t, moduli=[int(x) for x in g["moduli"]])
+    ctx = par.context_at_level(0)
+    a = [oracle.Ciphertext.from_array(par, x, 0) for x in g["a"]]
+    b = [oracle.Ciphertext.from_array(par, x, 0) for x in g["b"]]
+    assert (np.stack([x.sub(y).to_array() for x, y in zip(a, b)]) == g["sub"]).all()
+    assert (np.stack([x.copy().switch_to_level(2).to_array() for x in a]) == g["switch_to_2"]).all()
+    pts = [oracle.Poly(ctx, oracle.NTT, x.copy()) for x in g["dot_pts"]]
+    for grp in range(2):
+        assert (oracle.dot_product_scalar(a[2 * grp:2 * grp + 2], pts[2 * grp:2 * grp + 2]).to_array() == g["dot"][grp]).all()
+    basis = [int(x) for x in g["basis"]]
+    P = 1
+    for q in basis[3:]:
+        P *= q
+    m2 = oracle.Multiplicator(par, oracle.ScalingFactor.one(), oracle.ScalingFactor(P, ctx.modulus()), basis,
+                              oracle.ScalingFactor(t, P))
+    assert (np.stack([m2.multiply(x, y).to_array() for x, y in zip(a, b)]) == g["strategy2"]).all()
+    k2 = oracle.KeySwitchingKey.from_arrays(par, g["k2_c0"], g["k2_c1"], 2, 2)
+    ctx2 = par.context_at_level(2)
+    for x, exp in zip(g["k2_in"], g["k2_out"]):
+        c0, c1 = k2.key_switch(oracle.Poly(ctx2, oracle.POWER_BASIS, x.copy()))
+        assert (c0.c == exp[0]).all() and (c1.c == exp[1]).all()
+    # meaning: decrypt with the stored secret key
+    sk = oracle.SecretKey(par, np.random.default_rng(0))
+    sk.coeffs = g["sk"]
+    ma = oracle.simd_decode(par, sk.decrypt(a[0])).astype(np.int64)
+    mb = oracle.simd_decode(par, sk.decrypt(b[0])).astype(np.int64)
+    dec = lambda arr, lvl=0: oracle.simd_decode(par, sk.decrypt(oracle.Ciphertext.from_array(par, arr, lvl))).astype(np.int64)
+    assert (dec(g["sub"][0]) == (ma - mb) % t).all() and (dec(g["neg"][0]) == (-ma) % t).all()
+    assert (dec(g["switch_to_2"][0], 2) == ma).all()
+    assert (dec(g["strategy2"][0]) == (ma * mb) % t).all() and (dec(g["strategy2_relin"][0]) == (ma * mb) % t).all()
+    assert (dec(g["mul_3x2"][0]) == (ma * mb * mb) % t).all()

@@ -395,6 +395,38 @@ def test_golden_fixture(oracle, F):
     assert (F.Ciphertext.from_host(gpar, g["a"]).into_power_basis().to_host() == g["a_pb"]).all()
 
 
+def test_wide_golden_fixture(F):
+    """committed golden vectors of the operations around the core (tests/golden/make_golden_wide.py): device ==
+    stored outputs, no oracle involved"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_n16_l3_wide.npz"))
+    t = int(g["t"])
+    gpar = F.BfvParameters(int(g["degree"]), t, moduli=[int(x) for x in g["moduli"]])
+    A, B = F.Ciphertext.from_host(gpar, g["a"]), F.Ciphertext.from_host(gpar, g["b"])
+    assert ((A - B).to_host() == g["sub"]).all() and ((-A).to_host() == g["neg"]).all()
+    assert (A.clone().switch_down().to_host() == g["switch_down"]).all()
+    assert (A.clone().switch_to_level(2).to_host() == g["switch_to_2"]).all()
+    assert (A.clone().add_plain(g["pt_to_poly"]).to_host() == g["add_plain"]).all()
+    assert (A.clone().sub_plain(g["pt_to_poly"]).to_host() == g["sub_plain"]).all()
+    assert (A.clone().mul_plain(g["pt_poly_ntt"]).to_host() == g["mul_plain"]).all()
+    assert (F.dot_product_scalar(A, g["dot_pts"], 2).to_host() == g["dot"]).all()
+    assert (((A * B) * B).to_host() == g["mul_3x2"]).all()
+    basis = [int(x) for x in g["basis"]]
+    P, Q = 1, 1
+    for q in basis[3:]:
+        P *= q
+    for q in basis[:3]:
+        Q *= q
+    m2 = F.Multiplicator.new(F.ScalingFactor.one(), F.ScalingFactor(P, Q), basis, F.ScalingFactor(t, P), gpar)
+    assert (m2.multiply(A, B).to_host() == g["strategy2"]).all()
+    m2.enable_relinearization(F.RelinearizationKey.from_arrays(gpar, g["rk_c0"], g["rk_c1"]))
+    assert (m2.multiply(A, B).to_host() == g["strategy2_relin"]).all()
+    k2 = F.KeySwitchingKey.from_arrays(gpar, g["k2_c0"], g["k2_c1"], ciphertext_level=2, key_level=2)
+    X = F.Ciphertext.from_host(gpar, g["k2_in"][:, None], level=2, repr=F.POWER_BASIS)
+    assert (k2.key_switch(X, 0).to_host() == g["k2_out"]).all()
+    assert (A.to_packed()[0] == g["packed"]).all()
+
+
 @pytest.mark.parametrize("env", [{"FHE_B200_SOLINAS_NTT": "1"}, {"FHE_B200_NO_SOLINAS": "1"}, {"FHE_B200_GENERIC_NTT": "1"},
                                  {"FHE_B200_CHUNK": "1"}, {"FHE_B200_ROWS_TLOG": "12", "FHE_B200_COLS_TLOG": "12"}])
 def test_alternate_code_paths(F, env):
