@@ -376,7 +376,7 @@ def main():
                                    "frac": rows * (NTT_CFG["degree"] // 2) * 14 / (ntt_ms * 1e-3) / 1e12 / 0.961}}
 
     if rank == 0:
-        cpu = None if args.no_cpu_baseline else cpu_baseline_sample()
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_sample()   # rank 0, N = 1 only
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
