@@ -84,6 +84,7 @@ struct fhe_b200_params {
   T* to_dev(const std::vector<T>& v) const {
     if (device < 0 || v.empty()) return nullptr;
     T* d = nullptr;
+    FHE_CUDA(cudaSetDevice(device));   // tables are built lazily, possibly from a thread whose current device differs
     FHE_CUDA(cudaMalloc(&d, v.size() * sizeof(T)));
     const_cast<fhe_b200_params*>(this)->d_allocs.push_back(d);
     FHE_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
