@@ -174,6 +174,34 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _oracle_set_c():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fhe_oracle as O
+    return O, O.BfvParameters(DEGREE, PLAINTEXT, moduli_sizes=[62] * N_MODULI)
+
+
+def verify_against_oracle(np, A, Bt, out, rot, kc, gc, indices):
+    """Outside the timed region: download operands and results of a few ciphertexts whose indices span the internal
+    128-ciphertext chunks and compare them bit for bit with the CPU oracle (the checker, never the thing measured).
+    `rot` (nullable) is the rotated batch of A under the Galois key gc."""
+    O, opar = _oracle_set_c()
+    om = O.Multiplicator.default(O.RelinearizationKey.from_ksk(O.KeySwitchingKey.from_arrays(opar, kc[0], kc[1])))
+    ogk = O.GaloisKey.__new__(O.GaloisKey)
+    ogk.exponent, ogk.ksk = 3, O.KeySwitchingKey.from_arrays(opar, gc[0], gc[1])
+    one = np.empty((1, 2, N_MODULI, DEGREE), np.uint64)
+    ok_mul, ok_rot = True, True
+    for i in indices:
+        a = A.to_host(one.copy(), first=i)[0]
+        b = Bt.to_host(one.copy(), first=i)[0]
+        got = out.to_host(one.copy(), first=i)[0]
+        exp = om.multiply(O.Ciphertext.from_array(opar, a, 0), O.Ciphertext.from_array(opar, b, 0)).to_array()
+        ok_mul &= bool((got == exp).all())
+        if rot is not None:
+            gr = rot.to_host(one.copy(), first=i)[0]
+            ok_rot &= bool((gr == ogk.relinearize(O.Ciphertext.from_array(opar, a, 0)).to_array()).all())
+    return ok_mul, ok_rot
+
+
 def cpu_baseline_sample():
     """single-thread oracle port on a bounded sample (3 products at the full size)"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -243,7 +271,10 @@ def main():
     for i, q in enumerate(moduli):
         kc[:, :, i, :] = rng.integers(0, q, size=(2, N_MODULI, DEGREE), dtype=np.uint64)
     rk = F.RelinearizationKey.from_arrays(par, kc[0], kc[1])
-    mult = F.Multiplicator.default(rk)
+    gc = np.zeros((2, N_MODULI, N_MODULI, DEGREE), np.uint64)
+    for i, q in enumerate(moduli):
+        gc[:, :, i, :] = rng.integers(0, q, size=(2, N_MODULI, DEGREE), dtype=np.uint64)
+    gk = F.GaloisKey.from_arrays(par, 3, gc[0], gc[1])     # column rotation by one (evaluation_key.rs:118)
     out = F.Ciphertext(par, B, 2)
 
     def step():
@@ -275,6 +306,50 @@ def main():
     ms = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- BASELINE configs[3]: GaloisKey rotate (exponent 3) of the same batch, CUDA events, same barriers
+    rot = F.Ciphertext(par, B, 2)
+
+    def rot_step():
+        check(L.fhe_b200_galois(A._h, 3, gk.ksk._h, rot._h, None))
+    for _ in range(2):
+        rot_step()
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rot_steps = max(1, min(args.steps, 5))
+    r0.record()
+    for _ in range(rot_steps):
+        rot_step()
+    r1.record()
+    barrier()
+    rot_ms = torch.tensor([r0.elapsed_time(r1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(rot_ms, op=dist.ReduceOp.MAX)
+    rot_ms = float(rot_ms.item()) / rot_steps
+
+    # ---- parity of the timed work, outside the timed region: products / rotations whose indices span the internal
+    # chunks are compared with the CPU oracle on every rank; no `value` is printed unless all of them are bit-exact
+    idx = sorted(set(i for i in ((0, 127, 128, B - 1) if rank == 0 else (0, B - 1)) if 0 <= i < B))
+    ok_mul, ok_rot = verify_against_oracle(np, A, Bt, out, rot, kc, gc, idx)
+    okt = torch.tensor([int(ok_mul), int(ok_rot)], device="cuda")
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    ok_mul, ok_rot = bool(okt[0].item()), bool(okt[1].item())
+    assert ok_mul, "timed mul+relin products differ from the oracle"
+    assert ok_rot, "timed rotations differ from the oracle"
+
+    # ct + ct (the HBM-bound member of the family): rot += out, 3 rows of traffic per limb row
+    for _ in range(2):
+        check(L.fhe_b200_add(rot._h, out._h, None))
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(10):
+        check(L.fhe_b200_add(rot._h, out._h, None))
+    a1.record()
+    barrier()
+    add_ms = a0.elapsed_time(a1) / 10
+    del rot
 
     # ---- end to end through the public host API (C ABI) with HOST buffers: every step uploads the step's
     # operands from pinned host memory, multiplies, and downloads the products; chunks of 32 pairs rotate over
@@ -309,8 +384,11 @@ def main():
 
     e2e_step()
     barrier()
-    assert bool((ho[: wpc] == torch.as_tensor(DevArray(out.device_ptr(), wpc), device="cuda").cpu()).all()), \
-        "e2e result differs from the device-resident run"
+    # the end-to-end products must equal the device-resident ones (verified against the oracle above): first and
+    # last product of the first chunk, first of the second chunk (another stream / slot), last of the batch
+    for k in sorted(set((0, ch - 1, min(ch, Be - 1), Be - 1))):
+        dev = torch.as_tensor(DevArray(out.device_ptr() + k * wpc * 8, wpc), device="cuda").cpu()
+        assert bool((ho[k * wpc:(k + 1) * wpc] == dev).all()), "e2e product %d differs from the device-resident run" % k
     e2e_step()   # second warm-up pass: the stream-ordered pool has now seen the three-stream pattern
     barrier()
     e2e_steps = max(1, min(args.steps, 5))
@@ -392,8 +470,27 @@ def main():
                     "step_ms": [round(x * 1e3, 2) for x in step_s],
                     "pinned_copy_gbs": {"h2d": round(pcie["h2d"], 1), "d2h": round(pcie["d2h"], 1)}, "host_numa": numa},
             "gpu_launches": int(launches),
+            "verified": {"against": "CPU oracle (oracle/fhe_oracle), outside the timed region", "bit_exact": True,
+                         "mul_relin_indices": idx, "rotate_indices": idx,
+                         "e2e_vs_device_indices": sorted(set((0, ch - 1, min(ch, Be - 1), Be - 1))),
+                         "ranks": world},
             "roofline": roof,
+            "secondary": {
+                "rotate": {"workload": "BASELINE configs[3]: n=2^15, 14x62-bit, GaloisKey rotate (exponent 3), batch %d per GPU" % B,
+                           "value": world * B / (rot_ms * 1e-3), "unit": "rotations/s", "ms_per_step": rot_ms,
+                           "steps": rot_steps,
+                           "roofline": {"bound": "hbm", "unit": "GB/s", "algorithmic_mb_per_rotate": 143.0,
+                                        "achieved": 143.0e-3 * B / (rot_ms * 1e-3), "peak": peaks()[0],
+                                        "frac": 143.0e-3 * B / (rot_ms * 1e-3) / peaks()[0],
+                                        "note": "SURVEY 8d stage model: 2 gathers, L iNTT, L^2 digit NTTs, inner product, add"}},
+                "add": {"workload": "ct + ct, batch %d" % B, "value": B / (add_ms * 1e-3), "unit": "ct/s (one GPU)",
+                        "roofline": {"bound": "hbm", "unit": "GB/s", "algorithmic_mb_per_add": 22.0,
+                                     "achieved": 22.0e-3 * B / (add_ms * 1e-3), "peak": peaks()[0],
+                                     "frac": 22.0e-3 * B / (add_ms * 1e-3) / peaks()[0]}},
+            },
             "cpu_baseline": cpu,
+            "vs_single_thread": None if cpu is None else {"device_resident": value / cpu["value"],
+                                                          "e2e": e2e_value / cpu["value"], "cores": 1},
         }
         print(json.dumps(line))
     if world > 1:

@@ -66,6 +66,7 @@ SYMBOLS = {
     "fhe_b200_key_switch": (_i, [_vp, _u32, _vp, _vp, _vp]),
     "fhe_b200_scale": (_i, [_vp, _i, _vp, _vp]),
     "fhe_b200_poly_packed_bytes": (_i, [_vp, _u32, C.POINTER(C.c_size_t)]),
+    "fhe_b200_batch_packed_bytes": (_i, [_vp, C.POINTER(C.c_size_t)]),
     "fhe_b200_batch_pack": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "fhe_b200_batch_unpack": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "fhe_b200_sync": (_i, [_vp]),

@@ -232,20 +232,35 @@ class Ciphertext:
         check(_capi.lib().fhe_b200_sync(stream))
         return ct
 
+    def _check_words(self, words: np.ndarray, first: int):
+        """[n][parts][limbs][N] contiguous u64 with first + n <= count -- anything else would overrun a buffer"""
+        shape = self.shape()
+        if words.dtype != np.uint64 or not words.flags["C_CONTIGUOUS"]:
+            raise FheError(_capi.INVALID_ARGUMENT, "expected a C-contiguous uint64 array")
+        if words.ndim != 4 or tuple(words.shape[1:]) != tuple(shape[1:]):
+            raise FheError(_capi.INVALID_ARGUMENT, "expected [n][%d][%d][%d] words" % tuple(shape[1:]))
+        if first < 0 or first + words.shape[0] > shape[0]:
+            raise FheError(_capi.INVALID_ARGUMENT, "range exceeds batch")
+
     def upload(self, words: np.ndarray, first: int = 0):
         words = np.ascontiguousarray(words, dtype=np.uint64)
+        self._check_words(words, first)
         check(_capi.lib().fhe_b200_batch_upload(self._h, first, words.shape[0], _ptr(words), self.stream))
+        check(_capi.lib().fhe_b200_sync(self.stream))   # `words` may be a temporary: do not return before it is read
 
-    def to_host(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def to_host(self, out: Optional[np.ndarray] = None, first: int = 0) -> np.ndarray:
+        """ciphertexts [first, first + len(out)) (all of them from `first` on when out is None)"""
         if out is None:
-            out = np.empty(self.shape(), np.uint64)
-        check(_capi.lib().fhe_b200_batch_download(self._h, 0, out.shape[0], _ptr(out), self.stream))
+            shape = self.shape()
+            out = np.empty((shape[0] - first,) + tuple(shape[1:]), np.uint64)
+        self._check_words(out, first)
+        check(_capi.lib().fhe_b200_batch_download(self._h, first, out.shape[0], _ptr(out), self.stream))
         return out
 
     # -- wire format (rq/convert.rs:17-131): Rq.coefficients blobs, one per polynomial
     def packed_bytes_per_poly(self) -> int:
         n = C.c_size_t()
-        check(_capi.lib().fhe_b200_poly_packed_bytes(self.par._h, self.level, C.byref(n)))
+        check(_capi.lib().fhe_b200_batch_packed_bytes(self._h, C.byref(n)))   # per batch: a mul-basis batch has L + E limbs
         return n.value
 
     def to_packed(self) -> np.ndarray:

@@ -76,6 +76,9 @@ struct fhe_b200_params {
   std::vector<LimbDev> h_limbs;
   LimbDev* d_limbs = nullptr;
   std::vector<void*> d_allocs;
+  // scratch of the batched operations comes from a stream-ordered pool this parameter set owns (the device's default
+  // pool, which a host application may be using for its own cudaMallocAsync calls, is left untouched)
+  cudaMemPool_t pool = nullptr;
   mutable std::mutex mu;
   mutable std::map<u32, std::unique_ptr<LevelData>> levels;
   mutable std::map<u32, int*> perms;
@@ -84,9 +87,16 @@ struct fhe_b200_params {
   T* to_dev(const std::vector<T>& v) const {
     if (device < 0 || v.empty()) return nullptr;
     T* d = nullptr;
-    FHE_CUDA(cudaSetDevice(device));   // tables are built lazily, possibly from a thread whose current device differs
+    // tables are built lazily, possibly from a thread whose current device differs: select ours, put theirs back
+    struct Restore {
+      int prev = -1;
+      ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore;
+    if (cudaGetDevice(&restore.prev) != cudaSuccess) { cudaGetLastError(); restore.prev = -1; }
+    if (restore.prev == device) restore.prev = -1;
+    else FHE_CUDA(cudaSetDevice(device));
     FHE_CUDA(cudaMalloc(&d, v.size() * sizeof(T)));
-    const_cast<fhe_b200_params*>(this)->d_allocs.push_back(d);
+    const_cast<fhe_b200_params*>(this)->d_allocs.push_back(d);   // owned from here on (freed with the set)
     FHE_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return d;
   }
@@ -224,8 +234,15 @@ void params_release(const fhe_b200_params* cp) {
   fhe_b200_params* p = const_cast<fhe_b200_params*>(cp);
   if (!p || p->refs.fetch_sub(1) != 1) return;
   if (p->device >= 0) {
+    int prev = -1;
+    cudaGetDevice(&prev);
     cudaSetDevice(p->device);
     for (void* d : p->d_allocs) cudaFree(d);
+    if (p->pool) {
+      cudaDeviceSynchronize();   // scratch freed with cudaFreeAsync must have retired before its pool goes away
+      cudaMemPoolDestroy(p->pool);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
     cudaGetLastError();
   }
   delete p;
@@ -266,21 +283,38 @@ LimbDev make_limb_dev(u64 q, const NttTablesH& t, ToDev&& to_dev) {
   return d;
 }
 
+// selects the parameter set's device for the duration of an API call and puts the caller's device back afterwards
 struct DeviceGuard {
+  int prev = -1;
   explicit DeviceGuard(const fhe_b200_params* p) {
     if (p->device < 0) throw FheError(FHE_B200_NO_DEVICE, "parameter set was created without a CUDA device");
-    FHE_CUDA(cudaSetDevice(p->device));
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != p->device) FHE_CUDA(cudaSetDevice(p->device));
+    else prev = -1;
   }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
-// stream-ordered scratch memory
+// owning device pointer for the construction of handles (released on commit)
+struct DevPtr {
+  void* p = nullptr;
+  ~DevPtr() { if (p) { cudaFree(p); cudaGetLastError(); } }
+  void* release() { void* r = p; p = nullptr; return r; }
+};
+
+// stream-ordered scratch memory from the parameter set's own pool
 struct Workspace {
   cudaStream_t st;
+  cudaMemPool_t pool;
   std::vector<void*> ptrs;
-  explicit Workspace(cudaStream_t s) : st(s) {}
+  Workspace(const fhe_b200_params* par, cudaStream_t s) : st(s), pool(par->pool) {}
   u64* words(size_t n) {
     void* p = nullptr;
-    FHE_CUDA(cudaMallocAsync(&p, n * sizeof(u64), st));
+    FHE_CUDA(cudaMallocFromPoolAsync(&p, n * sizeof(u64), pool, st));
     ptrs.push_back(p);
     return (u64*)p;
   }
@@ -503,7 +537,13 @@ static int params_build(int device, uint32_t degree, const std::vector<u64>& mod
   REQUIRE(degree >= 8 && degree <= 65536 && (degree & (degree - 1)) == 0, FHE_B200_INVALID_DEGREE,
           "InvalidPolynomialDegree: " + std::to_string(degree));
   REQUIRE(!moduli.empty() && moduli.size() < 32, FHE_B200_INVALID_ARGUMENT, "MissingCiphertextModulusSpecification");
-  std::unique_ptr<fhe_b200_params> p(new fhe_b200_params());
+  // released through params_release on every exit path (frees the device tables and the pool of a half-built set)
+  std::unique_ptr<fhe_b200_params, void (*)(const fhe_b200_params*)> p(new fhe_b200_params(), params_release);
+  struct Restore {   // the caller's current device is left as it was
+    int prev = -1;
+    ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+  } restore;
+  if (device >= 0 && cudaGetDevice(&restore.prev) != cudaSuccess) { cudaGetLastError(); restore.prev = -1; }
   p->device = device;
   p->N = degree;
   p->logn = (u32)__builtin_ctz(degree);
@@ -542,15 +582,19 @@ static int params_build(int device, uint32_t degree, const std::vector<u64>& mod
       throw FheError(FHE_B200_NO_DEVICE, "CUDA device " + std::to_string(device) + " not available");
     }
     FHE_CUDA(cudaSetDevice(device));
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      // scratch freed on one stream must not be handed to another stream through an inserted dependency: that
-      // serialises callers that pipeline chunks over several streams (bench.py e2e); let each stream keep its own
-      int off = 0;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
-    }
+    cudaMemPoolProps props;
+    std::memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    FHE_CUDA(cudaMemPoolCreate(&p->pool, &props));
+    unsigned long long thr = ~0ull;   // keep freed scratch for the next chunk instead of returning it to the OS
+    FHE_CUDA(cudaMemPoolSetAttribute(p->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // scratch freed on one stream must not be handed to another stream through an inserted dependency: that
+    // serialises callers that pipeline chunks over several streams (bench.py e2e); let each stream keep its own
+    int off = 0;
+    FHE_CUDA(cudaMemPoolSetAttribute(p->pool, cudaMemPoolReuseAllowInternalDependencies, &off));
   }
   for (size_t i = 0; i < p->primes.size(); i++) {
     u64 q = p->primes[i];
@@ -738,11 +782,13 @@ int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uin
   k->par = p; k->ct_level = ciphertext_level; k->ksk_level = ksk_level; k->n_dig = n_digits; k->Lk = kl.L;
   k->log_base = log_base;
   size_t bytes = ((size_t)n_digits * kl.L << p->logn) * sizeof(u64);
-  k->k0 = k->k1 = nullptr;
-  FHE_CUDA(cudaMalloc(&k->k0, bytes));
-  FHE_CUDA(cudaMalloc(&k->k1, bytes));
-  FHE_CUDA(cudaMemcpy(k->k0, c0, bytes, cudaMemcpyHostToDevice));
-  FHE_CUDA(cudaMemcpy(k->k1, c1, bytes, cudaMemcpyHostToDevice));
+  DevPtr g0, g1;   // freed again if anything below fails
+  FHE_CUDA(cudaMalloc(&g0.p, bytes));
+  FHE_CUDA(cudaMalloc(&g1.p, bytes));
+  FHE_CUDA(cudaMemcpy(g0.p, c0, bytes, cudaMemcpyHostToDevice));
+  FHE_CUDA(cudaMemcpy(g1.p, c1, bytes, cudaMemcpyHostToDevice));
+  k->k0 = (u64*)g0.release();
+  k->k1 = (u64*)g1.release();
   params_retain(p);
   *out = k.release();
   API_END
@@ -800,13 +846,14 @@ static int plain_op(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_po
   const fhe_b200_params* par = a->par;
   DeviceGuard g(par);
   cudaStream_t st = (cudaStream_t)stream;
-  Workspace ws(st);
+  Workspace ws(par, st);
   const size_t words = ((size_t)n_polys * a->limbs) << par->logn;
   u64* pt = ws.words(words);
   FHE_CUDA(cudaMemcpyAsync(pt, host_polys, words * sizeof(u64), cudaMemcpyHostToDevice, st));
   launch_mul_plain(a->d, pt, a->count, a->parts, n_polys, ids_of(a), par->d_limbs, par->logn, st, op);
   FHE_CUDA(cudaGetLastError());
-  FHE_CUDA(cudaStreamSynchronize(st));   // host_polys may be pageable: do not return before it has been read
+  // No synchronisation: a pageable host_polys has been staged by the runtime when cudaMemcpyAsync returns; a pinned
+  // one must stay valid until the stream reaches this point -- the same contract as fhe_b200_batch_upload.
   API_END
 }
 int fhe_b200_mul_plain(fhe_b200_batch* a, const uint64_t* host_polys, uint32_t n_polys, void* stream) {
@@ -857,7 +904,7 @@ int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batc
   const u32 na = a->parts, nb = b->parts, nc = na + nb - 1;
   for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
     u32 n = std::min(chunk_size(), a->count - c0);
-    Workspace ws(st);
+    Workspace ws(par, st);
     u64* o = out3->d + (size_t)c0 * nc * lv.L * row;
     const u64* pa = a->d + (size_t)c0 * na * lv.L * row;
     const u64* pb = b->d + (size_t)c0 * nb * lv.L * row;
@@ -892,7 +939,7 @@ int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_
   const size_t row = (size_t)1 << par->logn, L = lv.L;
   for (u32 c0 = 0; c0 < ct3->count; c0 += chunk_size()) {
     u32 n = std::min(chunk_size(), ct3->count - c0);
-    Workspace ws(st);
+    Workspace ws(par, st);
     const u64* src = ct3->d + (size_t)c0 * 3 * L * row;
     u64* dst = out2->d + (size_t)c0 * 2 * L * row;
     u64* c2 = ws.words((size_t)n * L * row);
@@ -933,7 +980,7 @@ int fhe_b200_mul_relin(const fhe_b200_batch* a, const fhe_b200_batch* b, const f
   const size_t row = (size_t)1 << par->logn, L = lv.L;
   for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
     u32 n = std::min(chunk_size(), a->count - c0);
-    Workspace ws(st);
+    Workspace ws(par, st);
     u64* o = mod_switch ? ws.words((size_t)n * 2 * L * row) : out2->d + (size_t)c0 * 2 * L * row;
     u64* c2 = ws.words((size_t)n * L * row);
     mul_core(par, lv, a->d + (size_t)c0 * 2 * L * row, b->d + (size_t)c0 * 2 * L * row, n, o, c2, 1, ws, st);
@@ -1074,7 +1121,7 @@ int fhe_b200_multiplicator_multiply(const fhe_b200_multiplicator* m, const fhe_b
   const size_t row = (size_t)1 << par->logn, L = lv.L;
   for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
     const u32 n = std::min(chunk_size(), a->count - c0);
-    Workspace ws(st);
+    Workspace ws(par, st);
     const bool direct = !rk && !mod_switch;
     u64* W = direct ? out->d + (size_t)c0 * 3 * L * row : ws.words((size_t)n * 3 * L * row);
     mul_core_general(m, a->d + (size_t)c0 * 2 * L * row, b->d + (size_t)c0 * 2 * L * row, n, W, ws, st);
@@ -1140,7 +1187,7 @@ int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_
   const int* perm = par->perm(exponent);
   for (u32 c0 = 0; c0 < ct->count; c0 += chunk_size()) {
     u32 n = std::min(chunk_size(), ct->count - c0);
-    Workspace ws(st);
+    Workspace ws(par, st);
     const u64* src = ct->d + (size_t)c0 * 2 * L * row;
     u64* dst = out->d + (size_t)c0 * 2 * L * row;
     u64* s = ws.words((size_t)n * 2 * L * row);
@@ -1173,7 +1220,7 @@ int fhe_b200_key_switch(const fhe_b200_batch* pb, uint32_t part, const fhe_b200_
   const size_t row = (size_t)1 << par->logn, L = pb->limbs, Lk = k->Lk;
   for (u32 c0 = 0; c0 < pb->count; c0 += chunk_size()) {
     u32 n = std::min(chunk_size(), pb->count - c0);
-    Workspace ws(st);
+    Workspace ws(par, st);
     u64* c2 = ws.words((size_t)n * L * row);
     FHE_CUDA(cudaMemcpy2DAsync(c2, L * row * 8, pb->d + ((size_t)c0 * pb->parts + part) * L * row,
                                pb->parts * L * row * 8, L * row * 8, n, cudaMemcpyDeviceToDevice, st));
@@ -1197,15 +1244,15 @@ int fhe_b200_switch_down(fhe_b200_batch* b, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const LevelData& nl = par->level(b->level + 1);
   const u32 polys = b->count * b->parts;
-  u64* nd = nullptr;
-  FHE_CUDA(cudaMalloc(&nd, ((size_t)polys * nl.L << par->logn) * sizeof(u64)));
+  // Stream-ordered and in place: the L-1 surviving rows of every polynomial go through scratch memory and the forward
+  // transform writes them back, compacted, at the start of the batch's own allocation (which keeps its size: the
+  // pointer handed out by fhe_b200_batch_device_ptr stays valid, nothing is allocated, freed or synchronised here).
+  Workspace ws(par, st);
+  u64* tmp = ws.words((size_t)polys * nl.L << par->logn);
   launch_ntt(b->d, b->d, polys * lv.L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
-  launch_switch_down(lv.sd, b->d, nd, polys, lv.L, lv.ctx_ids, par->d_limbs, par->logn, st);
-  launch_ntt(nd, nd, polys * nl.L, nl.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
+  launch_switch_down(lv.sd, b->d, tmp, polys, lv.L, lv.ctx_ids, par->d_limbs, par->logn, st);
+  launch_ntt(tmp, b->d, polys * nl.L, nl.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
   FHE_CUDA(cudaGetLastError());
-  FHE_CUDA(cudaStreamSynchronize(st));
-  cudaFree(b->d);
-  b->d = nd;
   b->level += 1;
   b->limbs = nl.L;
   API_END
@@ -1227,7 +1274,7 @@ int fhe_b200_scale(const fhe_b200_batch* in, int which, fhe_b200_batch* out, voi
   const LevelData& lv = par->level(in->level);
   const size_t row = (size_t)1 << par->logn;
   const u32 polys = in->count * in->parts;
-  Workspace ws(st);
+  Workspace ws(par, st);
   u64* pb = ws.words((size_t)polys * in->limbs * row);
   launch_ntt(in->d, pb, polys * in->limbs, ids_of(in), par->d_limbs, par->logn, true, 1, false, st);
   if (which == 0) {  // extender: common prefix copied, E new rows computed (rq/scaler.rs:61-65, :85-115)
@@ -1278,6 +1325,12 @@ int fhe_b200_poly_packed_bytes(const fhe_b200_params* p, uint32_t level, size_t*
   *nbytes = n;
   API_END
 }
+int fhe_b200_batch_packed_bytes(const fhe_b200_batch* b, size_t* nbytes) {
+  API_BEGIN
+  REQUIRE(b && nbytes, FHE_B200_INVALID_ARGUMENT, "null argument");
+  *nbytes = pack_desc(b).poly_bytes;
+  API_END
+}
 int fhe_b200_batch_pack(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint8_t* host_out, void* stream) {
   API_BEGIN
   REQUIRE(b && host_out, FHE_B200_INVALID_ARGUMENT, "null argument");
@@ -1287,7 +1340,7 @@ int fhe_b200_batch_pack(const fhe_b200_batch* b, uint32_t first, uint32_t n, uin
   cudaStream_t st = (cudaStream_t)stream;
   const PackDev P = pack_desc(b);
   const size_t rows = (size_t)n * b->parts * b->limbs, row = (size_t)1 << par->logn;
-  Workspace ws(st);
+  Workspace ws(par, st);
   const u64* src = b->d + b->words_per_ct() * first;
   if (b->repr == FHE_B200_NTT) {   // rq/convert.rs:20-24: serialization is always in power basis
     u64* pb = ws.words(rows * row);
@@ -1311,7 +1364,7 @@ int fhe_b200_batch_unpack(fhe_b200_batch* b, uint32_t first, uint32_t n, const u
   cudaStream_t st = (cudaStream_t)stream;
   const PackDev P = pack_desc(b);
   const size_t rows = (size_t)n * b->parts * b->limbs;
-  Workspace ws(st);
+  Workspace ws(par, st);
   const size_t nbytes = (size_t)n * b->parts * P.poly_bytes;
   unsigned char* dbytes = (unsigned char*)ws.words((nbytes + 7) / 8);
   FHE_CUDA(cudaMemcpyAsync(dbytes, host_in, nbytes, cudaMemcpyHostToDevice, st));

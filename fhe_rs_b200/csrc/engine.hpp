@@ -19,6 +19,11 @@ struct CudaFail {
     if (e__ != cudaSuccess) throw CudaFail{e__, #x};        \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: remember, per (device, kernel),
+// the largest size already granted and raise it when a launch needs more (thread-safe; a parameter set may live on
+// any device of the process).  Throws CudaFail when the device refuses.
+void ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 // position -> limb id map of the rows of a buffer
 struct RowIds {
   u32 limbs_per_poly;
@@ -28,8 +33,12 @@ struct RowIds {
 // ---- NTT (ntt.cu)
 // Transforms n_rows rows of N words.  in may differ from out (first pass reads in).
 // in_div / reduce_on_load / lazy_out: see NttArgs.
+// digit_adjacent (forward, in_div == limbs_per_poly only): polynomial p = (ct, digit d) writes its limb-j row at
+// ((ct*limbs_per_poly + j)*n_dig + d)*N instead of (p*limbs_per_poly + j)*N -- the layout the key-switch inner
+// product reads fastest (all digits of one (ct, limb) adjacent).
 void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
-                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out = false);
+                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out = false,
+                bool digit_adjacent = false, u32 n_dig = 1);
 
 // ---- element-wise (kernels.cu)
 enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2 };

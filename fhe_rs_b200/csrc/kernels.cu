@@ -735,11 +735,7 @@ void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* 
   }
   const size_t n_out4 = (n_out + 3) & ~(size_t)3, nf = S.n_from;
   const size_t smem = (nf * kScaleTC + nf * n_out4 + n_out4 + 5 * nf) * sizeof(u64);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  ensure_dynamic_smem((const void*)scale_kernel, smem);
   scale_kernel<<<polys * (N / kScaleTC), kScaleTC, smem, st>>>(A);
   g_launches++;
 }

@@ -1,13 +1,33 @@
 // NTT launcher: picks the (N1, N2) split and tile shapes for a given N and instantiates
 // the tile kernels of ntt.cuh.
+#include <algorithm>
+#include <cstdint>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "engine.hpp"
 #include "ntt_fast.cuh"
+#include "ntt_tma.cuh"
 
 namespace fhe_b200 {
 
 std::atomic<unsigned long long> g_launches{0};
+
+void ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return;   // the default limit needs no opt-in
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;
+  int dev = 0;
+  FHE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  size_t& have = granted[std::make_pair(dev, kernel)];
+  if (have >= bytes) return;
+  FHE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  have = bytes;
+}
 
 namespace {
 
@@ -34,11 +54,7 @@ void run_cols(const NttArgs& a, cudaStream_t st) {
 template <int LOGP, bool COLS, bool INV, int TLOG = 12>
 void run_fast(const NttArgs& a, cudaStream_t st) {
   constexpr size_t smem = 2 * FastTile<LOGP, COLS, INV, false, TLOG>::TW * sizeof(u64);
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    cudaFuncSetAttribute(ntt_fast_kernel<LOGP, COLS, INV, TLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  ensure_dynamic_smem((const void*)ntt_fast_kernel<LOGP, COLS, INV, TLOG>, smem);
   constexpr int LOGB = TLOG - LOGP;
   const u32 tiles = COLS ? ((1u << (a.logn - LOGP)) >> LOGB) : ((1u << a.logn1) >> LOGB);
   ntt_fast_kernel<LOGP, COLS, INV, TLOG><<<a.n_rows * tiles, 1 << (TLOG - 3), smem, st>>>(a);
@@ -82,10 +98,145 @@ void run_cols_for(const NttArgs& a, cudaStream_t st) {
   }
 }
 
+// ---- TMA-fed persistent kernels (ntt_tma.cuh)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  // the driver entry point is fetched through the runtime, so the library does not link against libcuda
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+struct TmaFail {};
+// the buffer [rows][N] u64 as 128-byte box rows: dims {16, rows*N/16}, box {16, box_rows}, 128-byte swizzle
+CUtensorMap rows_map(const u64* base, u64 rows, u32 logn, u32 box_rows) {
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {16, (rows << logn) >> 4};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {16, box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  if (gdim[1] >= (1ull << 31) ||
+      tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)base, gdim, gstride, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    throw TmaFail{};
+  return m;
+}
+// the buffer as [rows][N1][64] u64: box {16 columns, box_rows points, 1 row}, no swizzle
+CUtensorMap cols_map(const u64* base, u64 rows, u32 logn, u32 box_rows) {
+  CUtensorMap m;
+  const cuuint64_t gdim[3] = {64, (cuuint64_t)1 << (logn - 6), rows};
+  const cuuint64_t gstride[2] = {512, (cuuint64_t)8 << logn};
+  const cuuint32_t box[3] = {16, box_rows, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  if (tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)base, gdim, gstride, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    throw TmaFail{};
+  return m;
+}
+
+int sm_count() {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  int dev = 0;
+  FHE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  FHE_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  return cache[dev] = n;
+}
+
+constexpr int kRowsRlog = 4, kRowsStages = 4, kColsStages = 3;
+
+template <bool INV>
+void run_tma_rows(const u64* in, u64 in_rows, u64* out, u64 out_rows, NttTmaArgs A, cudaStream_t st) {
+  using Cfg = RowsCfg<kRowsRlog, kRowsStages>;
+  const CUtensorMap mi = rows_map(in, in_rows, A.logn, 4 * Cfg::R), mo = rows_map(out, out_rows, A.logn, 4 * Cfg::R);
+  A.tiles_per_row = (1u << (A.logn - 6)) / Cfg::R;
+  A.tiles_total = A.lpp * A.tiles_per_row * A.n_polys;
+  auto k = ntt_tma_rows_kernel<INV, kRowsRlog, kRowsStages>;
+  ensure_dynamic_smem((const void*)k, Cfg::SMEM);
+  const u32 grid = std::min<u64>(A.tiles_total, (u64)sm_count() * 4);
+  k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(mi, mo, A);
+  g_launches++;
+}
+template <int LOGP, bool INV>
+void run_tma_cols(const u64* in, u64 in_rows, u64* out, u64 out_rows, NttTmaArgs A, cudaStream_t st) {
+  using Cfg = ColsCfg<LOGP, kColsStages>;
+  const CUtensorMap mi = cols_map(in, in_rows, A.logn, Cfg::BOX_ROWS), mo = cols_map(out, out_rows, A.logn, Cfg::BOX_ROWS);
+  A.tiles_per_row = 4;
+  A.tiles_total = A.lpp * 4 * A.n_polys;
+  auto k = ntt_tma_cols_kernel<LOGP, INV, kColsStages>;
+  ensure_dynamic_smem((const void*)k, Cfg::SMEM);
+  const u32 per_sm = LOGP == 9 ? 1 : LOGP == 8 ? 2 : 4;
+  const u32 grid = std::min<u64>(A.tiles_total, (u64)sm_count() * per_sm);
+  k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(mi, mo, A);
+  g_launches++;
+}
+template <bool INV>
+void run_tma_cols_for(const u64* in, u64 in_rows, u64* out, u64 out_rows, const NttTmaArgs& A, cudaStream_t st) {
+  switch (A.logn - 6) {
+    case 7: run_tma_cols<7, INV>(in, in_rows, out, out_rows, A, st); break;
+    case 8: run_tma_cols<8, INV>(in, in_rows, out, out_rows, A, st); break;
+    case 9: run_tma_cols<9, INV>(in, in_rows, out, out_rows, A, st); break;
+    default: throw TmaFail{};
+  }
+}
+
+// Both passes through the TMA kernels.  Returns false when the shape is outside their domain (the caller then uses
+// the register-resident kernels).
+bool launch_ntt_tma(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn, bool inverse,
+                    u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out, bool digit_adjacent, u32 n_dig) {
+  const u32 lpp = ids.limbs_per_poly;
+  if (logn < 13 || logn > 15 || !tensor_map_encoder()) return false;
+  if (n_rows % lpp != 0 || (in_div != 1 && in_div != lpp)) return false;
+  if (digit_adjacent && ((n_rows / lpp) % n_dig != 0 || n_dig == 0)) return false;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 127) return false;
+  NttTmaArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.limbs = limbs;
+  A.n_polys = n_rows / lpp;
+  A.lpp = lpp;
+  A.logn = logn;
+  A.digit_adjacent = digit_adjacent ? 1 : 0;
+  A.n_dig = digit_adjacent ? n_dig : 1;
+  for (int i = 0; i < kMaxPos; i++) A.ids[i] = ids.ids[i];
+  const u64 in_rows = in_div == 1 ? n_rows : n_rows / lpp;
+  try {
+    NttTmaArgs first = A, second = A;
+    first.in_bcast = in_div != 1;
+    if (!inverse) {
+      first.reduce_on_load = reduce_on_load;
+      second.lazy_out = lazy_out;
+      run_tma_cols_for<false>(in, in_rows, out, n_rows, first, st);
+      run_tma_rows<false>(out, n_rows, out, n_rows, second, st);
+    } else {
+      if (reduce_on_load || in_div != 1) return false;
+      run_tma_rows<true>(in, in_rows, out, n_rows, first, st);
+      run_tma_cols_for<true>(out, n_rows, out, n_rows, second, st);
+    }
+  } catch (const TmaFail&) {
+    return false;
+  }
+  return true;
+}
+
 }  // namespace
 
 void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
-                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out) {
+                bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out, bool digit_adjacent,
+                u32 n_dig) {
   if (n_rows == 0) return;
   NttArgs a;
   a.in = in;
@@ -109,6 +260,21 @@ void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const Li
   second.in = out;
   second.in_div = 1;
   second.reduce_on_load = 0;
+  // TMA-fed persistent kernels: the default whenever a launch carries enough polynomials per limb to amortise the
+  // per-(limb, tile position) twiddle staging; FHE_B200_NTT=fast keeps the register-resident kernels, =tma forces
+  // the TMA ones for any batch size (tests)
+  static const int tma_mode = [] {
+    const char* e = getenv("FHE_B200_NTT");
+    if (e && !strcmp(e, "fast")) return 0;
+    if (e && !strcmp(e, "tma")) return 2;
+    return 1;
+  }();
+  static const bool other_family = getenv("FHE_B200_GENERIC_NTT") != nullptr || getenv("FHE_B200_SOLINAS_NTT") != nullptr;
+  if (tma_mode && !other_family && (tma_mode == 2 || n_rows / ids.limbs_per_poly >= 8) &&
+      launch_ntt_tma(in, out, n_rows, ids, limbs, logn, inverse, in_div, reduce_on_load, st, lazy_out, digit_adjacent,
+                     n_dig))
+    return;
+  if (digit_adjacent) throw CudaFail{cudaErrorNotSupported, "digit-adjacent NTT output needs the TMA kernels"};
   // the register-resident kernels carry the Shoup butterflies only (the Solinas form measured no faster and doubled
   // their code size); FHE_B200_SOLINAS_NTT therefore selects the generic tile kernels, which keep both
   static const bool generic = getenv("FHE_B200_GENERIC_NTT") != nullptr || getenv("FHE_B200_SOLINAS_NTT") != nullptr;

@@ -103,7 +103,9 @@ int fhe_b200_batch_alloc(const fhe_b200_params* p, uint32_t count, uint32_t part
 int fhe_b200_batch_free(fhe_b200_batch* b);
 int fhe_b200_batch_info(const fhe_b200_batch* b, uint32_t* count, uint32_t* parts, uint32_t* level,
                         uint32_t* limbs, int* repr);
-/* host <-> device copy of ciphertexts [first, first+n); host may be pageable or pinned. */
+/* host <-> device copy of ciphertexts [first, first+n); host may be pageable or pinned.  Uploads (and the host_polys
+ * of fhe_b200_mul_plain / fhe_b200_add_plain) are only enqueued: a pinned source must stay valid until `stream` has
+ * passed the call (a pageable one has been staged by the CUDA runtime when the call returns). */
 int fhe_b200_batch_upload(fhe_b200_batch* b, uint32_t first, uint32_t n, const uint64_t* host, void* stream);
 int fhe_b200_batch_download(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint64_t* host, void* stream);
 /* same as download, but only enqueues the copy on `stream` (host must be pinned for it to be asynchronous);
@@ -184,7 +186,9 @@ int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_
                     fhe_b200_batch* out, void* stream);
 /* Poly::substitute on every row of an NTT batch (rq/mod.rs:360-389) */
 int fhe_b200_substitute(const fhe_b200_batch* in, uint32_t exponent, fhe_b200_batch* out, void* stream);
-/* Ciphertext::switch_down: drop the last modulus with rounding (ciphertext.rs:148-161, rq/mod.rs:433-492) */
+/* Ciphertext::switch_down: drop the last modulus with rounding (ciphertext.rs:148-161, rq/mod.rs:433-492).
+ * Stream-ordered and in place: the batch keeps its allocation (fhe_b200_batch_device_ptr stays valid, the words of the
+ * lower level are compacted at its start), nothing is allocated or synchronised. */
 int fhe_b200_switch_down(fhe_b200_batch* b, void* stream);
 /* KeySwitchingKey::key_switch on part `part` of a POWER_BASIS batch (key_switching_key.rs:241-270):
  * out (2 parts, NTT, ksk level) = (sum_i NTT(d_i) * c0_i, sum_i NTT(d_i) * c1_i) */
@@ -206,6 +210,9 @@ int fhe_b200_batch_alloc_mul_basis(const fhe_b200_params* p, uint32_t count, uin
  * The protobuf framing itself (tags, varints, `representation`, `degree`) stays with the host's prost code. */
 /* Modulus::serialization_length summed over the limbs of `level` (rq/convert.rs:78-82): bytes per polynomial */
 int fhe_b200_poly_packed_bytes(const fhe_b200_params* p, uint32_t level, size_t* nbytes);
+/* the same for the polynomials of one batch -- use this one to size the host buffers of pack / unpack: a batch over
+ * the multiplication basis (fhe_b200_batch_alloc_mul_basis) has L + E limbs, not the level's L */
+int fhe_b200_batch_packed_bytes(const fhe_b200_batch* b, size_t* nbytes);
 /* From<&Poly<R>> for Rq (rq/convert.rs:17-44): polynomials of ciphertexts [first, first+n) -> power basis
  * (if the batch is NTT) -> packed bytes; host_out receives n*parts blobs of packed_bytes each. */
 int fhe_b200_batch_pack(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint8_t* host_out, void* stream);

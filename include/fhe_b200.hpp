@@ -161,7 +161,7 @@ class Ciphertext {
   // Rq.coefficients of every polynomial (rq/convert.rs:17-44): count*parts blobs of packed_bytes() each
   size_t packed_bytes() const {
     size_t n = 0;
-    check(fhe_b200_poly_packed_bytes(par_->handle(), level(), &n));
+    check(fhe_b200_batch_packed_bytes(h_, &n));   // per batch: a multiplication-basis batch has L + E limbs
     return n;
   }
   std::vector<uint8_t> to_packed() const {

@@ -428,7 +428,9 @@ def test_wide_golden_fixture(F):
 
 
 @pytest.mark.parametrize("env", [{"FHE_B200_SOLINAS_NTT": "1"}, {"FHE_B200_NO_SOLINAS": "1"}, {"FHE_B200_GENERIC_NTT": "1"},
-                                 {"FHE_B200_CHUNK": "1"}, {"FHE_B200_ROWS_TLOG": "12", "FHE_B200_COLS_TLOG": "12"}])
+                                 {"FHE_B200_CHUNK": "1"}, {"FHE_B200_ROWS_TLOG": "12", "FHE_B200_COLS_TLOG": "12"},
+                                 {"FHE_B200_NTT": "tma"}, {"FHE_B200_NTT": "fast"},
+                                 {"FHE_B200_NTT": "tma", "FHE_B200_CHUNK": "1"}])
 def test_alternate_code_paths(F, env):
     """the optional arithmetic / kernel variants (Solinas twiddle pairs, Barrett-only folds, generic tile NTT,
     one-ciphertext chunks, 4096-word NTT tiles) must be bit-identical too: rerun the set-A multiply + the 2^13 NTT test under each switch"""
@@ -438,7 +440,8 @@ def test_alternate_code_paths(F, env):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
                           "test_mul_relin_against_oracle and 4096 or test_ntt_forward_backward and 13-2 or "
-                          "test_ntt_forward_backward and 15-2 or test_golden_fixture"],
+                          "test_ntt_forward_backward and 14-3 or test_ntt_forward_backward and 15-2 or "
+                          "test_golden_fixture or test_full_size_set_c or test_set_b_ntt_config"],
                          cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
@@ -699,3 +702,96 @@ def test_rgsw_external_product(oracle, F):
     got = grg.external_product(X).to_host()
     for i in range(3):
         assert (got[i] == org.external_product(octs[i]).to_array()).all()
+
+
+def _rand_rows(rng, moduli, shape_prefix, degree):
+    a = np.zeros(tuple(shape_prefix) + (len(moduli), degree), np.uint64)
+    for i, q in enumerate(moduli):
+        a[..., i, :] = rng.integers(0, q, size=tuple(shape_prefix) + (degree,), dtype=np.uint64)
+    return a
+
+
+@pytest.mark.parametrize("variant", ["plain", "mod_switch", "key_level_0_ct_level_1"])
+def test_set_c_across_chunk_boundary(oracle, F, variant):
+    """The shape the headline number is measured on (N = 2^15, 14 x 62-bit) with MORE ciphertexts than one internal
+    chunk (128): products 0, 127, 128, 129 of a 130-pair batch and rotations 0 / 128 / 129 are compared with the
+    oracle, so the chunk loop, its tail chunk and every per-chunk offset of mul_relin / galois are covered --
+    plain, with modulus switching (mul.rs:296-330), and with a level-0 key serving level-1 ciphertexts
+    (relinearization_key.rs:88-95, galois_key.rs:69-76)."""
+    degree, t, L = 1 << 15, 786433, 14
+    opar = oracle.BfvParameters(degree, t, moduli_sizes=[62] * L)
+    gpar = F.BfvParameters(degree, t, moduli_sizes=[62] * L)
+    rng = np.random.default_rng(77)
+    ct_level = 1 if variant == "key_level_0_ct_level_1" else 0
+    key_mod = opar.context_at_level(0).moduli
+    ct_mod = opar.context_at_level(ct_level).moduli
+    n_dig = len(ct_mod)
+    kc = _rand_rows(rng, key_mod, (2, n_dig), degree)      # [c0|c1][digit][key limb][N]
+    gc = _rand_rows(rng, key_mod, (2, n_dig), degree)
+    oksk = oracle.KeySwitchingKey.from_arrays(opar, kc[0], kc[1], ct_level, 0)
+    ork = oracle.RelinearizationKey.from_ksk(oksk)
+    grk = F.RelinearizationKey.from_arrays(gpar, kc[0], kc[1], ciphertext_level=ct_level, key_level=0)
+    ogk = oracle.GaloisKey.__new__(oracle.GaloisKey)
+    ogk.exponent, ogk.ksk = 3, oracle.KeySwitchingKey.from_arrays(opar, gc[0], gc[1], ct_level, 0)
+    ggk = F.GaloisKey.from_arrays(gpar, 3, gc[0], gc[1], ciphertext_level=ct_level, key_level=0)
+    count = 130
+    a = _rand_rows(rng, ct_mod, (count, 2), degree)
+    b = _rand_rows(rng, ct_mod, (count, 2), degree)
+    A = F.Ciphertext.from_host(gpar, a, level=ct_level)
+    B = F.Ciphertext.from_host(gpar, b, level=ct_level)
+    om, gm = oracle.Multiplicator.default(ork), F.Multiplicator.default(grk)
+    if variant == "mod_switch":
+        om.enable_mod_switching()
+        gm.enable_mod_switching()
+    out = gm.multiply(A, B)
+    assert out.level == ct_level + (1 if variant == "mod_switch" else 0)
+    P = out.to_host()
+    for i in (0, 127, 128, 129):
+        exp = om.multiply(oracle.Ciphertext.from_array(opar, a[i], ct_level),
+                          oracle.Ciphertext.from_array(opar, b[i], ct_level))
+        assert (P[i] == exp.to_array()).all(), "product %d differs" % i
+    R = ggk.relinearize(A).to_host()
+    for i in (0, 128, 129):
+        exp = ogk.relinearize(oracle.Ciphertext.from_array(opar, a[i], ct_level))
+        assert (R[i] == exp.to_array()).all(), "rotation %d differs" % i
+    if variant == "plain":
+        # &ct * &ct then relinearizes, across the boundary as well
+        C3 = A * B
+        R2 = grk.relinearizes(C3).to_host()
+        assert (R2 == P).all()
+
+
+def test_set_b_ntt_config(oracle, F):
+    """BASELINE configs[1]: N = 2^14, 8 x 62-bit.  (a) the full [256][8][2^14] buffer the roofline leg of bench.py
+    times: backward(forward(x)) == x on every word, and rows of forward(x) equal to the oracle's transform;
+    (b) one ct x ct mul + relinearize and one rotation against the oracle (ntt/mod.rs:50-82, mul.rs:263-330)."""
+    degree, t, L = 1 << 14, 786433, 8
+    opar = oracle.BfvParameters(degree, t, moduli_sizes=[62] * L)
+    gpar = F.BfvParameters(degree, t, moduli_sizes=[62] * L)
+    assert gpar.moduli() == opar.moduli
+    ctx = opar.context_at_level(0)
+    rng = np.random.default_rng(14)
+    x = _rand_rows(rng, ctx.moduli, (256, 1), degree)
+    X = F.Ciphertext.from_host(gpar, x, repr=F.POWER_BASIS)
+    fwd = X.into_ntt().to_host()
+    for c in (0, 100, 255):
+        for i, op in enumerate(ctx.ops):
+            e = x[c, 0, i].copy()
+            op.forward(e)
+            assert (fwd[c, 0, i] == e).all()
+    assert (X.into_power_basis().to_host() == x).all()
+    # mul + relin and rotation
+    kc, gc = _rand_rows(rng, ctx.moduli, (2, L), degree), _rand_rows(rng, ctx.moduli, (2, L), degree)
+    ork = oracle.RelinearizationKey.from_ksk(oracle.KeySwitchingKey.from_arrays(opar, kc[0], kc[1]))
+    grk = F.RelinearizationKey.from_arrays(gpar, kc[0], kc[1])
+    a, b = _rand_rows(rng, ctx.moduli, (3, 2), degree), _rand_rows(rng, ctx.moduli, (3, 2), degree)
+    A, B = F.Ciphertext.from_host(gpar, a), F.Ciphertext.from_host(gpar, b)
+    P = F.Multiplicator.default(grk).multiply(A, B).to_host()
+    om = oracle.Multiplicator.default(ork)
+    for i in (0, 2):
+        exp = om.multiply(oracle.Ciphertext.from_array(opar, a[i], 0), oracle.Ciphertext.from_array(opar, b[i], 0))
+        assert (P[i] == exp.to_array()).all()
+    ogk = oracle.GaloisKey.__new__(oracle.GaloisKey)
+    ogk.exponent, ogk.ksk = 3, oracle.KeySwitchingKey.from_arrays(opar, gc[0], gc[1])
+    R = F.GaloisKey.from_arrays(gpar, 3, gc[0], gc[1]).relinearize(A).to_host()
+    assert (R[1] == ogk.relinearize(oracle.Ciphertext.from_array(opar, a[1], 0)).to_array()).all()
