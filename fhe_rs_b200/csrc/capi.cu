@@ -353,6 +353,7 @@ void key_switch_core(const fhe_b200_params* par, const fhe_b200_ksk* k, const u6
   const LevelData& kl = par->level(k->ksk_level);
   const u32 L = k->n_dig, Lk = k->Lk;
   u64* inter = ws.words(((size_t)cts * L * Lk) << par->logn);
+  bool adjacent = false;
   if (k->log_base) {
     // key_switch_decomposition (key_switching_key.rs:323-362): the digits of the single residue, each below
     // 2^log_base < q, transformed lazily like the RNS digits
@@ -369,10 +370,13 @@ void key_switch_core(const fhe_b200_params* par, const fhe_b200_ksk* k, const u6
   const bool reduce = qmax > 4 * qmin - 1 || qmin < (1ull << 8);
   // forward_vt_lazy (rq/mod.rs:580): the digits stay in [0,4q_j); the lazy accumulator of the inner product takes
   // any 64-bit operand and reduces once
-  launch_ntt(c2, inter, cts * L * Lk, kl.ctx_ids, par->d_limbs, par->logn, false, Lk, reduce, st, true);
+  // with the TMA kernels the transform deposits the digits of one (ciphertext, limb) in adjacent rows, which the
+  // inner product streams fastest (bench_micro/stride_read.cu)
+  adjacent = Lk > 1 && ntt_uses_tma(cts * L * Lk, kl.ctx_ids, par->logn, Lk, c2, inter);
+  launch_ntt(c2, inter, cts * L * Lk, kl.ctx_ids, par->d_limbs, par->logn, false, Lk, reduce, st, true, adjacent, L);
   }
   launch_ksmac(inter, k->k0, k->k1, base0, base1, out0, out1, cts, L, Lk, out_ct_rows, kl.ctx_ids, par->d_limbs,
-               par->logn, st);
+               par->logn, st, adjacent);
 }
 
 // key switch + the reference's post-processing (relinearization_key.rs:88-95, galois_key.rs:69-76):
@@ -785,8 +789,14 @@ int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uin
   DevPtr g0, g1;   // freed again if anything below fails
   FHE_CUDA(cudaMalloc(&g0.p, bytes));
   FHE_CUDA(cudaMalloc(&g1.p, bytes));
-  FHE_CUDA(cudaMemcpy(g0.p, c0, bytes, cudaMemcpyHostToDevice));
-  FHE_CUDA(cudaMemcpy(g1.p, c1, bytes, cudaMemcpyHostToDevice));
+  // host layout [digit][limb][N] -> device layout [limb][digit][N]: the inner product walks the digits of one limb
+  const size_t rowb = sizeof(u64) << p->logn;
+  for (u32 i = 0; i < n_digits; i++) {
+    FHE_CUDA(cudaMemcpy2D((char*)g0.p + i * rowb, n_digits * rowb, (const char*)c0 + (size_t)i * kl.L * rowb, rowb, rowb,
+                          kl.L, cudaMemcpyHostToDevice));
+    FHE_CUDA(cudaMemcpy2D((char*)g1.p + i * rowb, n_digits * rowb, (const char*)c1 + (size_t)i * kl.L * rowb, rowb, rowb,
+                          kl.L, cudaMemcpyHostToDevice));
+  }
   k->k0 = (u64*)g0.release();
   k->k1 = (u64*)g1.release();
   params_retain(p);

@@ -89,11 +89,15 @@ void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* 
                   u32 out_rows_per_poly, u32 start, u32 n_out, int split3, u32 logn, cudaStream_t st);
 
 // key-switch inner product (key_switching_key.rs:256-268) on already transformed digits:
-// inter: [ct][n_dig][Lk][N] canonical NTT values; k0,k1: [n_dig][Lk][N];
+// inter: [ct][n_dig][Lk][N] NTT values (lazy, any 64-bit word), or [ct][Lk][n_dig][N] when `adjacent`;
+// k0,k1: [Lk][n_dig][N] (limb-major: the device copy of a key is transposed once at upload);
 // out0/out1 row (ct, j) at out + (ct*out_ct_rows + j)*N ; base0/base1 (nullable) same indexing.
 void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* base0, const u64* base1, u64* out0,
                   u64* out1, u32 cts, u32 n_dig, u32 Lk, u32 out_ct_rows, const RowIds& ids, const LimbDev* limbs,
-                  u32 logn, cudaStream_t st);
+                  u32 logn, cudaStream_t st, bool adjacent = false);
+
+// whether launch_ntt will take the TMA kernels for this shape (they can write the digit-adjacent layout)
+bool ntt_uses_tma(u32 n_rows, const RowIds& ids, u32 logn, u32 in_div, const u64* in, const u64* out);
 
 // base-2^log_base digit decomposition of single-limb polynomials (key_switching_key.rs:339-345):
 // in [polys][N] -> out [polys][n_dig][N]

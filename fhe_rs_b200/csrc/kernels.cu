@@ -486,13 +486,15 @@ struct KsMacArgs {
   const u64 *inter, *k0, *k1, *base0, *base1;
   u64 *out0, *out1;
   u32 cts, n_dig, Lk, out_ct_rows, logn;
+  u32 adjacent;   // digit rows of one (ciphertext, limb) adjacent: inter is [ct][limb][digit][N], else [ct][digit][limb][N]
   const LimbDev* limbs;
   unsigned short ids[kMaxPos];
 };
 // out0 = base0 + sum_i t_i * k0_i ; out1 = base1 + sum_i t_i * k1_i   (key_switching_key.rs:256-268)
 // One thread per (limb j, ciphertext, coefficient), limb-major: consecutive CTAs work on the same key limb for
-// every ciphertext of the chunk, so the 2 x n_dig key rows of that limb (7 MB at set C) stay in L2 while the digit
-// rows stream through -- each key word leaves HBM once per chunk instead of once per ciphertext.
+// every ciphertext of the chunk, so the 2 x n_dig key rows of that limb (7 MB at set C, stored limb-major
+// [limb][digit][N]) stay in L2 while the digit rows stream through -- each key word leaves HBM once per chunk instead
+// of once per ciphertext.
 __global__ void ksmac_kernel(KsMacArgs A) {
   const u32 N = 1u << A.logn;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over Lk*cts*N
@@ -505,27 +507,29 @@ __global__ void ksmac_kernel(KsMacArgs A) {
   Acc192 a0, a1;
   a0.clear();
   a1.clear();
-  const u64* t_ptr = A.inter + ((((size_t)ct * A.n_dig) * A.Lk + j) << A.logn) + c;
-  const u64* k0_ptr = A.k0 + ((size_t)j << A.logn) + c;
-  const u64* k1_ptr = A.k1 + ((size_t)j << A.logn) + c;
-  const size_t dstride = (size_t)A.Lk << A.logn;
+  const u64* t_ptr = A.adjacent ? A.inter + ((((size_t)ct * A.Lk + j) * A.n_dig) << A.logn) + c
+                                : A.inter + ((((size_t)ct * A.n_dig) * A.Lk + j) << A.logn) + c;
+  const size_t dstride = A.adjacent ? (size_t)1 << A.logn : (size_t)A.Lk << A.logn;
+  const size_t kstride = (size_t)1 << A.logn;
+  const u64* k0_ptr = A.k0 + (((size_t)j * A.n_dig) << A.logn) + c;
+  const u64* k1_ptr = A.k1 + (((size_t)j * A.n_dig) << A.logn) + c;
   // two digits per trip, the six words of the next trip requested before the multiplies of this one (the kernel
   // is bound by HBM latency, not by the multiplier: 2 x n_dig x 8 IMAD.WIDE per 48 bytes read).  Two
   // coefficients per thread with 16-byte accesses, and four ciphertexts per thread sharing each key word (a third
-  // of the L2 -> SM bytes), both measured the same or slower: ~3.0 TB/s of HBM reads either way (profiles/microbench_r1.txt)
+  // of the L2 -> SM bytes), both measured the same or slower (profiles/microbench_r1.txt)
   u32 i = 0;
   u64 t0 = 0, t1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
   if (A.n_dig >= 2) {
     t0 = t_ptr[0], t1 = t_ptr[dstride];
-    x0 = __ldg(k0_ptr), x1 = __ldg(k0_ptr + dstride);
-    y0 = __ldg(k1_ptr), y1 = __ldg(k1_ptr + dstride);
+    x0 = __ldg(k0_ptr), x1 = __ldg(k0_ptr + kstride);
+    y0 = __ldg(k1_ptr), y1 = __ldg(k1_ptr + kstride);
   }
   for (; i + 2 <= A.n_dig; i += 2) {
     const u64 ct0 = t0, ct1 = t1, cx0 = x0, cx1 = x1, cy0 = y0, cy1 = y1;
     if (i + 4 <= A.n_dig) {
       t0 = t_ptr[(size_t)(i + 2) * dstride], t1 = t_ptr[(size_t)(i + 3) * dstride];
-      x0 = __ldg(k0_ptr + (size_t)(i + 2) * dstride), x1 = __ldg(k0_ptr + (size_t)(i + 3) * dstride);
-      y0 = __ldg(k1_ptr + (size_t)(i + 2) * dstride), y1 = __ldg(k1_ptr + (size_t)(i + 3) * dstride);
+      x0 = __ldg(k0_ptr + (size_t)(i + 2) * kstride), x1 = __ldg(k0_ptr + (size_t)(i + 3) * kstride);
+      y0 = __ldg(k1_ptr + (size_t)(i + 2) * kstride), y1 = __ldg(k1_ptr + (size_t)(i + 3) * kstride);
     }
     a0.mac(ct0, cx0);
     a1.mac(ct0, cy0);
@@ -534,8 +538,8 @@ __global__ void ksmac_kernel(KsMacArgs A) {
   }
   if (i < A.n_dig) {
     const u64 tl = t_ptr[(size_t)i * dstride];
-    a0.mac(tl, __ldg(k0_ptr + (size_t)i * dstride));
-    a1.mac(tl, __ldg(k1_ptr + (size_t)i * dstride));
+    a0.mac(tl, __ldg(k0_ptr + (size_t)i * kstride));
+    a1.mac(tl, __ldg(k1_ptr + (size_t)i * kstride));
   }
   const size_t o = (((size_t)ct * A.out_ct_rows + j) << A.logn) + c;
   if (A.base0) a0.add64(A.base0[o]);
@@ -742,8 +746,9 @@ void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* 
 
 void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* base0, const u64* base1, u64* out0,
                   u64* out1, u32 cts, u32 n_dig, u32 Lk, u32 out_ct_rows, const RowIds& ids, const LimbDev* limbs,
-                  u32 logn, cudaStream_t st) {
+                  u32 logn, cudaStream_t st, bool adjacent) {
   KsMacArgs A;
+  A.adjacent = adjacent ? 1 : 0;
   A.inter = inter; A.k0 = k0; A.k1 = k1; A.base0 = base0; A.base1 = base1; A.out0 = out0; A.out1 = out1;
   A.cts = cts; A.n_dig = n_dig; A.Lk = Lk; A.out_ct_rows = out_ct_rows; A.logn = logn;
   A.limbs = limbs;

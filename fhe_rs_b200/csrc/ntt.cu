@@ -232,7 +232,29 @@ bool launch_ntt_tma(const u64* in, u64* out, u32 n_rows, const RowIds& ids, cons
   return true;
 }
 
+int tma_mode() {
+  static const int mode = [] {
+    const char* e = getenv("FHE_B200_NTT");
+    if (getenv("FHE_B200_GENERIC_NTT") || getenv("FHE_B200_SOLINAS_NTT")) return 0;
+    if (e && !strcmp(e, "fast")) return 0;
+    if (e && !strcmp(e, "tma")) return 2;
+    return 1;
+  }();
+  return mode;
+}
+
 }  // namespace
+
+// TMA-fed persistent kernels: the default whenever a launch carries enough polynomials per limb to amortise the
+// per-(limb, tile position) twiddle staging; FHE_B200_NTT=fast keeps the register-resident kernels, =tma forces the
+// TMA ones for any batch size (tests)
+bool ntt_uses_tma(u32 n_rows, const RowIds& ids, u32 logn, u32 in_div, const u64* in, const u64* out) {
+  const u32 lpp = ids.limbs_per_poly;
+  if (!tma_mode() || logn < 13 || logn > 15 || !tensor_map_encoder()) return false;
+  if (n_rows % lpp != 0 || (in_div != 1 && in_div != lpp)) return false;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 127) return false;
+  return tma_mode() == 2 || n_rows / lpp >= 8;
+}
 
 void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,
                 bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out, bool digit_adjacent,
@@ -260,17 +282,7 @@ void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const Li
   second.in = out;
   second.in_div = 1;
   second.reduce_on_load = 0;
-  // TMA-fed persistent kernels: the default whenever a launch carries enough polynomials per limb to amortise the
-  // per-(limb, tile position) twiddle staging; FHE_B200_NTT=fast keeps the register-resident kernels, =tma forces
-  // the TMA ones for any batch size (tests)
-  static const int tma_mode = [] {
-    const char* e = getenv("FHE_B200_NTT");
-    if (e && !strcmp(e, "fast")) return 0;
-    if (e && !strcmp(e, "tma")) return 2;
-    return 1;
-  }();
-  static const bool other_family = getenv("FHE_B200_GENERIC_NTT") != nullptr || getenv("FHE_B200_SOLINAS_NTT") != nullptr;
-  if (tma_mode && !other_family && (tma_mode == 2 || n_rows / ids.limbs_per_poly >= 8) &&
+  if (ntt_uses_tma(n_rows, ids, logn, in_div, in, out) &&
       launch_ntt_tma(in, out, n_rows, ids, limbs, logn, inverse, in_div, reduce_on_load, st, lazy_out, digit_adjacent,
                      n_dig))
     return;
