@@ -48,13 +48,19 @@ void upload_scaler_tables(ScalerData& s, const std::vector<u64>& to_moduli, ToDe
   d.to_lo = to_dev(s.h.theta_omega_lo);
   d.to_hi = to_dev(s.h.theta_omega_hi);
   d.to_sign = to_dev(s.h.theta_omega_sign);
-  // source indices of the theta_omega terms, positive sign first (the kernel makes one pass per sign)
+  // source indices of the theta_omega terms, positive sign first (the kernel makes one pass per sign).  Terms whose
+  // fractional part is exactly zero add nothing (rns/scaler.rs:282-298 multiplies them by zero) and are left out:
+  // in the down scaler of the multiplication basis that is every extension limb (garner_i * t / Q is an integer).
   std::vector<unsigned char> order;
+  d.n_pos = 0;
   for (int sg = 0; sg < 2; sg++)
     for (size_t i = 0; i < s.h.theta_omega_sign.size(); i++)
-      if ((int)s.h.theta_omega_sign[i] == sg) order.push_back((unsigned char)i);
-  d.n_pos = 0;
-  for (unsigned char v : s.h.theta_omega_sign) d.n_pos += v == 0;
+      if ((int)s.h.theta_omega_sign[i] == sg && (s.h.theta_omega_lo[i] | s.h.theta_omega_hi[i]) != 0) {
+        order.push_back((unsigned char)i);
+        d.n_pos += sg == 0;
+      }
+  d.n_terms = (u32)order.size();
+  if (order.empty()) order.push_back(0);   // keep the table non-empty (never read: n_terms == 0)
   d.to_order = to_dev(order);
   d.tgar_lo = to_dev(s.h.theta_garner_lo);
   d.tgar_hi = to_dev(s.h.theta_garner_hi);

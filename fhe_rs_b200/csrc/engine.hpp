@@ -77,7 +77,7 @@ struct ScalerDev {
   const u64* to_hi;
   const unsigned char* to_sign;
   const unsigned char* to_order;   // source indices, the theta_omega terms with positive sign first
-  u32 n_pos, pad2;
+  u32 n_pos, n_terms;              // positive-sign terms, all non-zero terms (<= n_from)
   const u64* tgar_lo;     // theta_garner [n_from]
   const u64* tgar_hi;
   unsigned short to_ids[kMaxPos];

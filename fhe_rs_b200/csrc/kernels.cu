@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
     s_tgh[i] = S.tgar_hi[i];
     s_tol[i] = S.to_lo[i];
     s_toh[i] = S.to_hi[i];
-    s_ord[i] = S.to_order[i];
+    s_ord[i] = i < S.n_terms ? S.to_order[i] : 0;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
     for (u32 sg = 0; sg < 2; sg++) {
       AccTheta at;
       at.clear();
-      const u32 k0 = sg ? S.n_pos : 0, k1 = sg ? nf : S.n_pos;
+      const u32 k0 = sg ? S.n_pos : 0, k1 = sg ? S.n_terms : S.n_pos;
 #pragma unroll 2
       for (u32 k = k0; k < k1; k++) {
         const u32 i = s_ord[k];

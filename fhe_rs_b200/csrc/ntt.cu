@@ -157,32 +157,70 @@ int sm_count() {
   return cache[dev] = n;
 }
 
-constexpr int kRowsRlog = 4, kRowsStages = 4, kColsStages = 3;
+constexpr int kRowsRlog = 4;
 
-template <bool INV>
-void run_tma_rows(const u64* in, u64 in_rows, u64* out, u64 out_rows, NttTmaArgs A, cudaStream_t st) {
-  using Cfg = RowsCfg<kRowsRlog, kRowsStages>;
+// shared-memory ring depth x resident CTAs per SM of the rows / cols kernels (FHE_B200_TMA_ROWS / _COLS = "SxB")
+int tma_variant(const char* env, int dflt) {
+  const char* e = getenv(env);
+  return e ? atoi(e) : dflt;
+}
+
+template <bool INV, int STAGES, int MINB>
+void run_tma_rows_v(const u64* in, u64 in_rows, u64* out, u64 out_rows, NttTmaArgs A, cudaStream_t st) {
+  using Cfg = RowsCfg<kRowsRlog, STAGES>;
   const CUtensorMap mi = rows_map(in, in_rows, A.logn, 4 * Cfg::R), mo = rows_map(out, out_rows, A.logn, 4 * Cfg::R);
   A.tiles_per_row = (1u << (A.logn - 6)) / Cfg::R;
   A.tiles_total = A.lpp * A.tiles_per_row * A.n_polys;
-  auto k = ntt_tma_rows_kernel<INV, kRowsRlog, kRowsStages>;
-  ensure_dynamic_smem((const void*)k, Cfg::SMEM);
-  const u32 grid = std::min<u64>(A.tiles_total, (u64)sm_count() * 4);
-  k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(mi, mo, A);
+  const u32 grid = std::min<u64>(A.tiles_total, (u64)sm_count() * MINB);
+  if (!INV && A.lazy_out) {
+    auto k = ntt_tma_rows_kernel<INV, kRowsRlog, STAGES, MINB, !INV>;
+    ensure_dynamic_smem((const void*)k, Cfg::SMEM);
+    k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(mi, mo, A);
+  } else {
+    auto k = ntt_tma_rows_kernel<INV, kRowsRlog, STAGES, MINB, false>;
+    ensure_dynamic_smem((const void*)k, Cfg::SMEM);
+    k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(mi, mo, A);
+  }
   g_launches++;
 }
-template <int LOGP, bool INV>
-void run_tma_cols(const u64* in, u64 in_rows, u64* out, u64 out_rows, NttTmaArgs A, cudaStream_t st) {
-  using Cfg = ColsCfg<LOGP, kColsStages>;
+template <bool INV>
+void run_tma_rows(const u64* in, u64 in_rows, u64* out, u64 out_rows, const NttTmaArgs& A, cudaStream_t st) {
+  static const int v = tma_variant("FHE_B200_TMA_ROWS", 44);
+  // (ring depth x CTAs per SM measured flat within 2% from 2x6 to 4x4, profiles/microbench_r2.txt)
+  if (v == 26) run_tma_rows_v<INV, 2, 6>(in, in_rows, out, out_rows, A, st);
+  else run_tma_rows_v<INV, 4, 4>(in, in_rows, out, out_rows, A, st);
+}
+template <int LOGP, bool INV, int STAGES, int MINB>
+void run_tma_cols_v(const u64* in, u64 in_rows, u64* out, u64 out_rows, NttTmaArgs A, cudaStream_t st) {
+  using Cfg = ColsCfg<LOGP, STAGES>;
   const CUtensorMap mi = cols_map(in, in_rows, A.logn, Cfg::BOX_ROWS), mo = cols_map(out, out_rows, A.logn, Cfg::BOX_ROWS);
   A.tiles_per_row = 4;
   A.tiles_total = A.lpp * 4 * A.n_polys;
-  auto k = ntt_tma_cols_kernel<LOGP, INV, kColsStages>;
-  ensure_dynamic_smem((const void*)k, Cfg::SMEM);
-  const u32 per_sm = LOGP == 9 ? 1 : LOGP == 8 ? 2 : 4;
-  const u32 grid = std::min<u64>(A.tiles_total, (u64)sm_count() * per_sm);
-  k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(mi, mo, A);
+  const u32 grid = std::min<u64>(A.tiles_total, (u64)sm_count() * MINB);
+  if (!INV && A.reduce_on_load) {
+    auto k = ntt_tma_cols_kernel<LOGP, INV, STAGES, MINB, !INV>;
+    ensure_dynamic_smem((const void*)k, Cfg::SMEM);
+    k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(mi, mo, A);
+  } else {
+    auto k = ntt_tma_cols_kernel<LOGP, INV, STAGES, MINB, false>;
+    ensure_dynamic_smem((const void*)k, Cfg::SMEM);
+    k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(mi, mo, A);
+  }
   g_launches++;
+}
+template <int LOGP, bool INV>
+void run_tma_cols(const u64* in, u64 in_rows, u64* out, u64 out_rows, const NttTmaArgs& A, cudaStream_t st) {
+  static const int v = tma_variant("FHE_B200_TMA_COLS", 3);
+  if (LOGP == 9) {
+    if (v == 2) run_tma_cols_v<9, INV, 2, 1>(in, in_rows, out, out_rows, A, st);
+    else run_tma_cols_v<9, INV, 3, 1>(in, in_rows, out, out_rows, A, st);
+  } else if (LOGP == 8) {
+    if (v == 2) run_tma_cols_v<8, INV, 2, 3>(in, in_rows, out, out_rows, A, st);
+    else run_tma_cols_v<8, INV, 3, 2>(in, in_rows, out, out_rows, A, st);
+  } else {
+    if (v == 2) run_tma_cols_v<7, INV, 2, 6>(in, in_rows, out, out_rows, A, st);
+    else run_tma_cols_v<7, INV, 3, 4>(in, in_rows, out, out_rows, A, st);
+  }
 }
 template <bool INV>
 void run_tma_cols_for(const u64* in, u64 in_rows, u64* out, u64 out_rows, const NttTmaArgs& A, cudaStream_t st) {

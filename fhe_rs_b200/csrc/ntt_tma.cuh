@@ -7,8 +7,7 @@
 //     no 64-bit address arithmetic at all -- on B200 those instructions compete with the butterflies for the integer
 //     multiplier pipe, which (not HBM) bounds this transform;
 //   * CTAs are persistent: each one walks a contiguous range of the launch's tiles through a ring of STAGES
-//     shared-memory buffers, so tile k+1 .. k+STAGES-2 are already in flight while tile k's butterflies run and the
-//     store of tile k-1 drains;
+//     shared-memory buffers, so tiles k+1 .. k+STAGES-1 are already in flight (or landed) while tile k's butterflies run;
 //   * the tiles of a launch are ordered limb-major, polynomial-minor, so consecutive tiles of a CTA use the SAME
 //     twiddles: they are staged in shared memory once per (limb, tile position) and read from there with
 //     `base + immediate` 128-bit loads (the rows pass used to fetch 16 KiB of twiddles from L2 per 8 KiB of data);
@@ -52,25 +51,26 @@ __device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
 __device__ __forceinline__ void mbar_arrive(u32 bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ u32 mbar_try_wait(u32 bar, u32 parity) {
+// one bounded wait: the hardware may suspend the thread for up to `ns` nanoseconds while the phase is incomplete
+__device__ __forceinline__ u32 mbar_try_wait(u32 bar, u32 parity, u32 ns) {
   u32 ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(ns)
       : "memory");
   return ok;
 }
-// a wait that cannot hang the device: a protocol error traps after ~2 s instead of spinning forever
+// a wait that cannot hang the device: a protocol error traps after a few seconds instead of spinning forever.  The
+// waiter sleeps inside try_wait (no instruction stream of polls competing with the butterflies for issue slots).
 __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+  u32 tries = 0;
+  while (!mbar_try_wait(bar, parity, 100000u)) {
+    if (++tries > 4000000u) __trap();
   }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -215,8 +215,9 @@ struct RowsCfg {
   static constexpr u32 SMEM = STAGES * TILE_BYTES + TW_PAIRS * 16 + 2 * STAGES * 8 + 1024;   // + alignment slack
 };
 
-template <bool INV, int RLOG, int STAGES>
-__global__ void __launch_bounds__(RowsCfg<RLOG, STAGES>::NT + 32)
+// LAZY (forward only): leave the outputs in [0,4p) (forward_vt_lazy, native.rs:142-181)
+template <bool INV, int RLOG, int STAGES, int MINB, bool LAZY>
+__global__ void __launch_bounds__(RowsCfg<RLOG, STAGES>::NT + 32, MINB)
     ntt_tma_rows_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                         const NttTmaArgs A) {
   using namespace tma;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(RowsCfg<RLOG, STAGES>::NT + 32)
       wl.next();
       loaded++;
     };
-    while (loaded < n && loaded < (u32)(STAGES - 1)) load_next();
+    while (loaded < n && loaded < (u32)STAGES) load_next();  // every buffer starts full
     for (u32 i = 0; i < n; i++) {
       const u32 s = i % STAGES;
       mbar_wait(bar_done + 8 * s, (i / STAGES) & 1);         // the consumers have finished tile i (in place)
@@ -272,8 +273,8 @@ __global__ void __launch_bounds__(RowsCfg<RLOG, STAGES>::NT + 32)
       bulk_commit();
       ws.next();
       if (loaded < n) {
-        bulk_wait_read<1>();                                 // every store but the newest has left shared memory:
-        load_next();                                         // the buffer of tile i-1 is free for tile i+STAGES-1
+        bulk_wait_read<0>();                                 // the store has left shared memory: its buffer takes
+        load_next();                                         // tile i+STAGES while tiles i+1 .. are being computed
       }
     }
     bulk_wait_all();
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(RowsCfg<RLOG, STAGES>::NT + 32)
 #pragma unroll
       for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw5 + 16 * 8 * R * m);
       fwd_stages<3>(v, tw, p, p2);
-      if (!A.lazy_out) {
+      if (!LAZY) {
 #pragma unroll
         for (int e = 0; e < 8; e++) v[e] = fwd_final<false>(v[e], p, p2, 0);
       }
@@ -422,9 +423,8 @@ struct ColsCfg {
 };
 
 // one radix-2^NS round (stages t .. t+NS-1 of the in-tile transform) over the whole tile, in place
-template <int LOGP, bool INV, int NS>
-__device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, int t, u64 p, u64 p2, const LimbDev& L,
-                                           bool reduce_on_load) {
+template <int LOGP, bool INV, int NS, bool REDUCE>
+__device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, int t, u64 p, u64 p2, const LimbDev& L) {
   using namespace tma;
   constexpr u32 NT = 1u << LOGP;
   constexpr int R = 1 << NS;
@@ -442,7 +442,7 @@ __device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, int t, u64 p, u
 #pragma unroll
     for (int e = 0; e < R; e++) {
       v[e] = lds64(addr + e * stride_bytes);
-      if (!INV && reduce_on_load) v[e] = barrett64(v[e], L.p, L.bhi, L.blo);
+      if (REDUCE) v[e] = barrett64(v[e], L.p, L.bhi, L.blo);
     }
     ulonglong2 tw[R - 1];
 #pragma unroll
@@ -462,8 +462,10 @@ __device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, int t, u64 p, u
   }
 }
 
-template <int LOGP, bool INV, int STAGES>
-__global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32)
+// REDUCE (forward only): reduce the source words modulo the row's prime as they are read (digit broadcast with
+// mixed modulus sizes, zq/mod.rs:756)
+template <int LOGP, bool INV, int STAGES, int MINB, bool REDUCE>
+__global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32, MINB)
     ntt_tma_cols_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                         const NttTmaArgs A) {
   using namespace tma;
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32)
       wl.next();
       loaded++;
     };
-    while (loaded < n && loaded < (u32)(STAGES - 1)) load_next();
+    while (loaded < n && loaded < (u32)STAGES) load_next();
     for (u32 i = 0; i < n; i++) {
       const u32 s = i % STAGES;
       mbar_wait(bar_done + 8 * s, (i / STAGES) & 1);
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32)
       bulk_commit();
       ws.next();
       if (loaded < n) {
-        bulk_wait_read<1>();
+        bulk_wait_read<0>();
         load_next();
       }
     }
@@ -558,15 +560,16 @@ __global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32)
     if (!INV) {
 #pragma unroll
       for (int r = 0; r < NR; r++) {
-        if (r < NR - 1) cols_round<LOGP, false, 3>(buf, tw_base, 3 * r, p, p2, *Lp, r == 0 && A.reduce_on_load);
-        else cols_round<LOGP, false, REM>(buf, tw_base, 3 * r, p, p2, *Lp, r == 0 && A.reduce_on_load);
+        if (r == 0) cols_round<LOGP, false, 3, REDUCE>(buf, tw_base, 0, p, p2, *Lp);
+        else if (r < NR - 1) cols_round<LOGP, false, 3, false>(buf, tw_base, 3 * r, p, p2, *Lp);
+        else cols_round<LOGP, false, REM, false>(buf, tw_base, 3 * r, p, p2, *Lp);
         if (r < NR - 1) consumer_sync<NT>();
       }
     } else {
 #pragma unroll
       for (int r = NR - 1; r >= 0; r--) {
-        if (r < NR - 1) cols_round<LOGP, true, 3>(buf, tw_base, 3 * r, p, p2, *Lp, false);
-        else cols_round<LOGP, true, REM>(buf, tw_base, 3 * r, p, p2, *Lp, false);
+        if (r < NR - 1) cols_round<LOGP, true, 3, false>(buf, tw_base, 3 * r, p, p2, *Lp);
+        else cols_round<LOGP, true, REM, false>(buf, tw_base, 3 * r, p, p2, *Lp);
         if (r > 0) consumer_sync<NT>();
       }
     }
