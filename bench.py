@@ -300,10 +300,8 @@ def main():
     ev1.record()
     barrier()
     launches = L.fhe_b200_launch_count() - l0
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    from fhe_rs_b200.shard import bind_host_thread_to_gpu, gather_checksums, max_over_ranks
+    ms = max_over_ranks(ev0.elapsed_time(ev1), device="cuda")     # device time of the slowest rank
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -322,10 +320,7 @@ def main():
         rot_step()
     r1.record()
     barrier()
-    rot_ms = torch.tensor([r0.elapsed_time(r1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(rot_ms, op=dist.ReduceOp.MAX)
-    rot_ms = float(rot_ms.item()) / rot_steps
+    rot_ms = max_over_ranks(r0.elapsed_time(r1), device="cuda") / rot_steps
 
     # ---- parity of the timed work, outside the timed region: products / rotations whose indices span the internal
     # chunks are compared with the CPU oracle on every rank; no `value` is printed unless all of them are bit-exact
@@ -337,6 +332,11 @@ def main():
     ok_mul, ok_rot = bool(okt[0].item()), bool(okt[1].item())
     assert ok_mul, "timed mul+relin products differ from the oracle"
     assert ok_rot, "timed rotations differ from the oracle"
+    # the one collective of the path: the (trivial) gather of results -- here one 63-bit checksum of every rank's
+    # product batch, NCCL all-gather in global shard order
+    n_out_words = B * 2 * N_MODULI * DEGREE
+    cs = int(torch.as_tensor(DevArray(out.device_ptr(), n_out_words), device="cuda").sum().item()) & ((1 << 63) - 1)
+    checksums = gather_checksums([cs], device="cuda")
 
     # ct + ct (the HBM-bound member of the family): rot += out, 3 rows of traffic per limb row
     for _ in range(2):
@@ -354,7 +354,6 @@ def main():
     # ---- end to end through the public host API (C ABI) with HOST buffers: every step uploads the step's
     # operands from pinned host memory, multiplies, and downloads the products; chunks of 32 pairs rotate over
     # several streams so that PCIe copies overlap the kernels of the other chunks
-    from fhe_rs_b200.shard import bind_host_thread_to_gpu
     numa = bind_host_thread_to_gpu(local)   # before the pinned staging buffers are allocated (first touch)
     Be = min(args.e2e_batch, B)
     ch = min(32, Be)
@@ -406,18 +405,38 @@ def main():
     step_s = sorted(float(x) for x in st_t.cpu())
     e2e_value = world * Be / step_s[len(step_s) // 2]
     words = Be * wpc
-    # what the box's PCIe link gives a plain pinned copy of the same buffers (diagnostic: e2e is link-bound)
+    # what the box gives plain pinned copies of the same buffers, every rank copying AT THE SAME TIME (diagnostic: the
+    # end-to-end path is bound by the host side of the links -- one link alone at N = 1, the host's aggregate at N = 8)
     dbuf = torch.empty(Be * wpc, dtype=torch.int64, device="cuda")
     pcie = {}
     for name, dst_, src_ in (("h2d", dbuf, ha), ("d2h", ho, dbuf)):
         dst_.copy_(src_, non_blocking=True)
-        torch.cuda.synchronize()
+        barrier()
         t1 = time.perf_counter()
         for _ in range(3):
             dst_.copy_(src_, non_blocking=True)
         torch.cuda.synchronize()
         pcie[name] = 3 * Be * wpc * 8 / (time.perf_counter() - t1) / 1e9
+    # both directions at once, as the pipelined end-to-end step drives them
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(3):
+        with torch.cuda.stream(s_up):
+            dbuf.copy_(ha, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            ho.copy_(torch.as_tensor(DevArray(out.device_ptr(), Be * wpc), device="cuda"), non_blocking=True)
+    torch.cuda.synchronize()
+    pcie["duplex_h2d"] = 3 * Be * wpc * 8 / (time.perf_counter() - t1) / 1e9
     del dbuf
+    per_rank = [None] * world
+    mine = {"rank": rank, "h2d": round(pcie["h2d"], 1), "d2h": round(pcie["d2h"], 1),
+            "duplex_h2d": round(pcie["duplex_h2d"], 1), "host_numa": numa,
+            "cpus": len(os.sched_getaffinity(0))}
+    if world > 1:
+        dist.all_gather_object(per_rank, mine)
+    else:
+        per_rank = [mine]
 
     # ---- roofline of the dominant kernel family (NTT), BASELINE config 2: [256][8][2^14] forward + inverse
     roof = None
@@ -468,12 +487,19 @@ def main():
                     "d2h_bytes_per_step": words * 8, "batch": Be, "streams": n_slots,
                     "timing": "median of %d steps (wall clock around upload+multiply+download, max over ranks)" % e2e_steps,
                     "step_ms": [round(x * 1e3, 2) for x in step_s],
-                    "pinned_copy_gbs": {"h2d": round(pcie["h2d"], 1), "d2h": round(pcie["d2h"], 1)}, "host_numa": numa},
+                    "pinned_copy_gbs": {"h2d": round(pcie["h2d"], 1), "d2h": round(pcie["d2h"], 1)}, "host_numa": numa,
+                    # every rank's plain pinned-copy rate with all ranks copying concurrently: their sum is the
+                    # host's aggregate ceiling for the end-to-end path (14.7 MB up + 7.3 MB down per product)
+                    "concurrent_pinned_copy_gbs_per_rank": per_rank,
+                    "aggregate_h2d_gbs": round(sum(r["duplex_h2d"] for r in per_rank), 1),
+                    "link_bound_products_per_s": round(sum(r["duplex_h2d"] for r in per_rank) * 1e9 / (2 * wpc * 8), 1)},
             "gpu_launches": int(launches),
             "verified": {"against": "CPU oracle (oracle/fhe_oracle), outside the timed region", "bit_exact": True,
                          "mul_relin_indices": idx, "rotate_indices": idx,
                          "e2e_vs_device_indices": sorted(set((0, ch - 1, min(ch, Be - 1), Be - 1))),
                          "ranks": world},
+            "result_gather": {"collective": "all_gather of one 63-bit checksum per rank (NCCL)" if world > 1 else "none (1 rank)",
+                              "checksums": checksums},
             "roofline": roof,
             "secondary": {
                 "rotate": {"workload": "BASELINE configs[3]: n=2^15, 14x62-bit, GaloisKey rotate (exponent 3), batch %d per GPU" % B,

@@ -43,6 +43,9 @@ void upload_scaler_tables(ScalerData& s, const std::vector<u64>& to_moduli, ToDe
   d.n_from = s.h.n_from; d.n_to = s.h.n_to; d.is_one = s.h.is_one; d.shift = s.h.shift;
   d.tg_lo = s.h.theta_gamma_lo; d.tg_hi = s.h.theta_gamma_hi; d.tg_sign = s.h.theta_gamma_sign;
   for (size_t j = 0; j < to_moduli.size(); j++) d.to_ids[j] = (unsigned short)index_of(to_moduli[j]);
+  d.all_solinas = getenv("FHE_B200_NO_SOLINAS") ? 0 : 1;
+  for (u64 q : to_moduli)
+    if ((q >> 61) != 1 || ((1ull << 62) - q) >= (1ull << 28)) d.all_solinas = 0;
   d.gamma = to_dev(s.h.gamma);
   d.omega = to_dev(s.h.omega);
   d.to_lo = to_dev(s.h.theta_omega_lo);

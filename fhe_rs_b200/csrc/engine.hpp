@@ -70,7 +70,8 @@ void launch_tensor_nm(const u64* a, const u64* b, const u64* xa, const u64* xb, 
 struct ScalerDev {
   u32 n_from, n_to, is_one, shift;
   u64 tg_lo, tg_hi;
-  u32 tg_sign, pad;
+  u32 tg_sign;
+  u32 all_solinas;   // every `to` limb is 2^62 - c, c < 2^28 (the persistent TMA kernel's epilogue needs it)
   const u64* gamma;       // [n_to]
   const u64* omega;       // [n_to][n_from]
   const u64* to_lo;       // theta_omega [n_from]

@@ -1,7 +1,16 @@
 // Element-wise ring ops, tensor product, exact RNS scaler, key-switch inner product,
 // Galois gather and modulus switch-down kernels (sm_100a).  64-bit integer modular
 // arithmetic, HBM / integer-pipe bound: no tensor cores.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
 #include "engine.hpp"
+#include "ntt_tma.cuh"
 
 namespace fhe_b200 {
 
@@ -417,6 +426,194 @@ __global__ void __launch_bounds__(kScaleTC) scale_kernel(ScaleArgs A) {
   }
 }
 
+
+// ------------------------------------------------------------------ exact RNS scaler, persistent TMA-fed form
+// Same arithmetic as scale_kernel (RnsScaler::scale, rns/scaler.rs:249-352: v and w "as coded", one lazy accumulator
+// and one reduction per output limb); what changes is everything around the multiply loop, which ran at 0.28 of the
+// multiplier-pipe bound while the loop itself ran at 0.87 (profiles/microbench_r1.txt):
+//   * persistent CTAs: the scaler tables (omega, gamma, theta_*, per-limb constants) are staged in shared memory once
+//     per CTA instead of once per 128-column tile;
+//   * the n_from x 128 source residues of a tile arrive with ONE TMA box copy (tensor map over [rows][N], box
+//     {128 columns, n_from rows}) tracked by an mbarrier; the next tile's copy is issued as soon as the last multiply
+//     group has read the current one;
+//   * the per-limb epilogue works on Solinas limbs only (q_j = 2^62 - c_j; the caller checks): v and w are folded with
+//     2^62 == c_j (one IMAD.WIDE each, no conditional subtraction, no canonical intermediate), -(v mod q_j)*gamma_j
+//     enters the accumulator as (2q_j - v')*gamma_j, +/-w as one 64-bit addend, and the per-limb constants come from
+//     shared memory (the old epilogue fetched the LimbDev record from global memory through two dependent loads).
+struct ScaleTmaArgs {
+  ScalerDev S;
+  const LimbDev* limbs;
+  u64 *out0, *out1;
+  u32 polys, out_rows_per_poly, start, n_out, split3, logn;
+  u32 tiles_total;   // polys * N / 128
+};
+
+template <bool IS_ONE>
+__global__ void __launch_bounds__(kScaleTC) scale_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const ScaleTmaArgs A) {
+  using namespace tma;
+  extern __shared__ __align__(128) u64 smem[];
+  const ScalerDev& S = A.S;
+  const u32 nf = S.n_from, n_out = A.n_out;
+  const u32 n_out4 = (n_out + 3) & ~3u;
+  constexpr u32 TC = kScaleTC;
+  u64* s_r = smem;                                // [n_from][TC]   (TMA destination, 128-byte aligned)
+  u64* s_omega = s_r + (size_t)nf * TC;           // [n_from][n_out4]  (transposed)
+  u64* s_gamma = s_omega + (size_t)nf * n_out4;   // [n_out4]
+  u64* s_p2 = s_gamma + n_out4;                   // [n_out4]  2 q_j
+  u64* s_c = s_p2 + n_out4;                       // [n_out4]  c_j = 2^62 - q_j
+  u64* s_tgl = s_c + n_out4;                      // theta_garner [n_from]
+  u64* s_tgh = s_tgl + nf;
+  u64* s_tol = s_tgh + nf;                        // theta_omega of the non-zero terms, positive sign first [n_terms]
+  u64* s_toh = s_tol + nf;
+  u32* s_ord = reinterpret_cast<u32*>(s_toh + nf);   // their source rows, as byte offsets into s_r
+  u64* s_bar = reinterpret_cast<u64*>(s_ord + ((nf + 1) & ~1u));
+  const u32 bar = smem_u32(s_bar);
+  const u32 cc = threadIdx.x;
+
+  for (u32 idx = cc; idx < nf * n_out4; idx += TC) {
+    const u32 ii = idx / n_out4, jj = idx - ii * n_out4;
+    s_omega[idx] = jj < n_out ? S.omega[(size_t)(A.start + jj) * nf + ii] : 0;
+  }
+  for (u32 i = cc; i < n_out4; i += TC) {
+    const bool live = i < n_out;
+    const LimbDev& M = A.limbs[S.to_ids[A.start + (live ? i : 0)]];
+    s_gamma[i] = live ? S.gamma[A.start + i] : 0;
+    s_p2[i] = M.p2;
+    s_c[i] = M.sol_c;
+  }
+  for (u32 i = cc; i < nf; i += TC) {
+    s_tgl[i] = S.tgar_lo[i];
+    s_tgh[i] = S.tgar_hi[i];
+    const u32 src = (!IS_ONE && i < S.n_terms) ? S.to_order[i] : 0;
+    s_tol[i] = IS_ONE ? 0 : S.to_lo[src];
+    s_toh[i] = IS_ONE ? 0 : S.to_hi[src];
+    s_ord[i] = src * TC * 8;
+  }
+  if (cc == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const u32 N = 1u << A.logn;
+  const u32 per_poly = N / TC;
+  const u32 dst_r = smem_u32(s_r);
+  const u32 tile_bytes = nf * TC * 8;
+  u32 tile = blockIdx.x;
+  if (cc == 0 && tile < A.tiles_total) {
+    mbar_expect_tx(bar, tile_bytes);
+    load_2d(dst_r, &tm_in, (tile % per_poly) * TC, (tile / per_poly) * nf, bar);
+  }
+  const u32 my_r = dst_r + cc * 8;   // this thread's column of the tile
+  for (u32 it = 0; tile < A.tiles_total; tile += gridDim.x, it++) {
+    const u32 poly = tile / per_poly;
+    const u32 c0 = (tile - poly * per_poly) * TC;
+    mbar_wait(bar, it & 1);
+
+    // v = round(sum_i r_i * theta_garner_i / 2^shift)   (:260-272)
+    u128 v;
+    {
+      AccTheta at;
+      at.clear();
+#pragma unroll 2
+      for (u32 i = 0; i < nf; i++) at.mac(lds64(my_r + i * TC * 8), s_tgl[i], s_tgh[i]);
+      u32 acc[7];
+      at.words(acc);
+      U256 sg = u256_from_acc(acc);
+      const u32 bs = S.shift - 1 - 64;
+      u64 lo = (sg.w1 >> bs) | (sg.w2 << (64 - bs));
+      u64 hi = (sg.w2 >> bs) | (sg.w3 << (64 - bs));
+      u128 x = ((u128)hi << 64) | lo;
+      v = (x >> 1) + (x & 1);
+    }
+    // w = round((sum_i +/- r_i * theta_omega_i -/+ v * theta_gamma) / 2^127)   (:276-314)
+    bool w_sign = false;
+    u128 w = 0;
+    if (!IS_ONE) {
+      U256 s_pos = {0, 0, 0, 0}, s_neg = {0, 0, 0, 0};
+#pragma unroll 1
+      for (u32 sg = 0; sg < 2; sg++) {
+        AccTheta at;
+        at.clear();
+        const u32 k0 = sg ? S.n_pos : 0, k1 = sg ? S.n_terms : S.n_pos;
+#pragma unroll 2
+        for (u32 k = k0; k < k1; k++) at.mac(lds64(my_r + s_ord[k]), s_tol[k], s_toh[k]);
+        u32 wds[7];
+        at.words(wds);
+        if (sg == 0) s_pos = u256_from_acc(wds);
+        else s_neg = u256_from_acc(wds);
+      }
+      U256 so = u256_sub(s_pos, s_neg);
+      U256 vt = u256_mul_128(v, S.tg_lo, S.tg_hi);
+      so = S.tg_sign ? u256_add(so, vt) : u256_sub(so, vt);
+      w_sign = (so.w3 != 0) || (so.w2 >> 63);
+      if (w_sign) {
+        u64 n1 = ~so.w1, n2 = ~so.w2, n3 = ~so.w3;
+        u128 y = ((u128)((n2 >> 62) | (n3 << 2)) << 64) | ((n1 >> 62) | (n2 << 2));
+        w = (y + 1) >> 1;
+      } else {
+        u128 y = ((u128)((so.w2 >> 62) | (so.w3 << 2)) << 64) | ((so.w1 >> 62) | (so.w2 << 2));
+        w = (y >> 1) + (y & 1);
+      }
+    }
+    // v = vh * 2^62 + vl, w likewise: modulo q_j = 2^62 - c_j they are vh * c_j + vl < 2 q_j
+    const u64 mask62 = (1ull << 62) - 1;
+    const u64 vl = (u64)v & mask62, wl = (u64)w & mask62;
+    const u32 vh = (u32)(v >> 62), wh = (u32)(w >> 62);
+
+    // destination of output limb 0 of this column
+    u64* dst;
+    size_t dstride = (size_t)1 << A.logn;
+    if (A.split3) {
+      const u32 ct = poly / 3, part = poly - ct * 3;
+      dst = part < 2 ? A.out0 + ((((size_t)ct * 2 + part) * n_out) << A.logn) : A.out1 + (((size_t)ct * n_out) << A.logn);
+    } else {
+      dst = A.out0 + (((size_t)poly * A.out_rows_per_poly) << A.logn);
+    }
+    dst += c0 + cc;
+
+    // outputs (:316-351): y_j = (-(v mod q_j) * gamma_j +/- w + sum_i r_i * omega_ji) mod q_j, four limbs at a time
+    for (u32 j0 = 0; j0 < n_out; j0 += 4) {
+      Acc192 acc[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[k].clear();
+      const ulonglong2* om = reinterpret_cast<const ulonglong2*>(s_omega + j0);
+      const u32 g = min(4u, n_out - j0);
+      switch (g) {
+        case 4: scale_mac_group<4>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+        case 3: scale_mac_group<3>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+        case 2: scale_mac_group<2>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+        default: scale_mac_group<1>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+      }
+      if (j0 + 4 >= n_out) {
+        // the tile has been read for the last time: fetch the next one while the last epilogue runs
+        __syncthreads();
+        const u32 nxt = tile + gridDim.x;
+        if (cc == 0 && nxt < A.tiles_total) {
+          mbar_expect_tx(bar, tile_bytes);
+          load_2d(dst_r, &tm_in, (nxt % per_poly) * TC, (nxt / per_poly) * nf, bar);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const u32 jj = j0 + k;
+        if (jj >= n_out) break;
+        const u64 p2 = s_p2[jj];
+        const u32 c = (u32)s_c[jj];
+        acc[k].mac(p2 - ((u64)vh * c + vl), s_gamma[jj]);      // -(v mod q) * gamma, as a positive multiple
+        if (!IS_ONE) {
+          const u64 wr = (u64)wh * c + wl;                     // w mod q in [0, 2q)
+          acc[k].add64(w_sign ? p2 - wr : wr);
+        }
+        u64 lo, mid;
+        u32 hi32;
+        acc[k].merged(lo, mid, hi32);
+        dst[(size_t)jj * dstride] = csub(fold192_solinas(lo, mid, hi32, c), p2 >> 1);
+      }
+    }
+  }
+}
+
 // fallback for rings smaller than one tile (N < 64): one thread per coefficient, same arithmetic
 __global__ void scale_small_kernel(ScaleArgs A) {
   const ScalerDev& S = A.S;
@@ -723,9 +920,81 @@ void launch_tensor_nm(const u64* a, const u64* b, const u64* xa, const u64* xb, 
   g_launches++;
 }
 
+namespace {
+typedef CUresult (*ScaleEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+ScaleEncodeFn scale_encoder() {
+  static ScaleEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (ScaleEncodeFn)p;
+  }();
+  return fn;
+}
+int scale_sm_count() {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  int dev = 0;
+  FHE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  FHE_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  return cache[dev] = n;
+}
+}  // namespace
+
+// The persistent TMA-fed kernel serves N >= 128 when every output limb is a Solinas prime (all 62-bit primes the
+// reference's parameter builder generates are); FHE_B200_SCALER=classic keeps the per-tile kernel.
+static bool launch_scale_tma(const ScalerDev& S, const LimbDev* limbs, const std::vector<u64>* sol_c_of_out, const u64* in,
+                             u64* out0, u64* out1, u32 polys, u32 out_rows_per_poly, u32 start, u32 n_out, int split3,
+                             u32 logn, cudaStream_t st) {
+  (void)sol_c_of_out;
+  static const bool classic = [] { const char* e = getenv("FHE_B200_SCALER"); return e && !strcmp(e, "classic"); }();
+  if (classic || !scale_encoder() || logn < 7 || (reinterpret_cast<uintptr_t>(in) & 127)) return false;
+  const u32 N = 1u << logn, nf = S.n_from;
+  if (nf > 64 || (u64)polys * nf >= (1ull << 31)) return false;
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {N, (cuuint64_t)polys * nf};
+  const cuuint64_t gstride[1] = {(cuuint64_t)8 << logn};
+  const cuuint32_t box[2] = {(cuuint32_t)kScaleTC, nf};
+  const cuuint32_t es[2] = {1, 1};
+  if (scale_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)in, gdim, gstride, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  ScaleTmaArgs A;
+  A.S = S; A.limbs = limbs; A.out0 = out0; A.out1 = out1;
+  A.polys = polys; A.out_rows_per_poly = out_rows_per_poly; A.start = start; A.n_out = n_out;
+  A.split3 = split3; A.logn = logn;
+  A.tiles_total = polys * (N / kScaleTC);
+  const size_t n_out4 = (n_out + 3) & ~(size_t)3;
+  const size_t smem = (nf * kScaleTC + nf * n_out4 + 3 * n_out4 + 4 * nf) * sizeof(u64) + ((nf + 1) & ~(size_t)1) * 4 + 16;
+  // persistent grid = exactly the CTAs that are resident at once (registers and shared memory both limit it)
+  auto resident = [&](const void* k) {
+    ensure_dynamic_smem(k, smem);
+    int per_sm = 0;
+    FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kScaleTC, smem));
+    return (u32)std::min<u64>(A.tiles_total, (u64)scale_sm_count() * std::max(per_sm, 1));
+  };
+  if (S.is_one) scale_tma_kernel<true><<<resident((const void*)scale_tma_kernel<true>), kScaleTC, smem, st>>>(tm, A);
+  else scale_tma_kernel<false><<<resident((const void*)scale_tma_kernel<false>), kScaleTC, smem, st>>>(tm, A);
+  g_launches++;
+  return true;
+}
+
 void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* out0, u64* out1, u32 polys,
                   u32 out_rows_per_poly, u32 start, u32 n_out, int split3, u32 logn, cudaStream_t st) {
   if (!polys || !n_out) return;
+  if (S.all_solinas && launch_scale_tma(S, limbs, nullptr, in, out0, out1, polys, out_rows_per_poly, start, n_out, split3,
+                                        logn, st))
+    return;
   ScaleArgs A;
   A.S = S; A.limbs = limbs; A.in = in; A.out0 = out0; A.out1 = out1;
   A.polys = polys; A.out_rows_per_poly = out_rows_per_poly; A.start = start; A.n_out = n_out;

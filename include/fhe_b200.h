@@ -208,6 +208,13 @@ int fhe_b200_batch_alloc_mul_basis(const fhe_b200_params* p, uint32_t count, uin
  * in order, the power-basis coefficients bit-packed LSB first with ceil(log2 q_i) bits each
  * (Modulus::serialize_vec zq/mod.rs:783-786, fhe_util::transcode_to_bytes fhe-util/src/lib.rs:71-108).
  * The protobuf framing itself (tags, varints, `representation`, `degree`) stays with the host's prost code. */
+/* Seeded ("compact") ciphertexts and keys are NOT expanded here.  The reference serialises a fresh ciphertext as c0 plus
+ * the 32-byte seed of c1 (bfv/ciphertext.rs:231-317; keys: key_switching_key.rs:365-482) and regenerates c1 with
+ * Poly::random_from_seed (rq/mod.rs:276-292): ChaCha8Rng::from_seed(seed) driving rand's uniform u64 sampling per
+ * limb.  That stream is defined by rand 0.10.2 / rand_chacha 0.10.0, which are not vendored in the reference tree
+ * and cannot be run or pinned in this build environment, so a device-side expansion could not be proven identical.
+ * The Rust host therefore expands c1 with the reference's own code (ciphertext.rs:287-300) and uploads both halves
+ * as words (fhe_b200_batch_upload) or as Rq blobs (fhe_b200_batch_unpack); the device never guesses the RNG. */
 /* Modulus::serialization_length summed over the limbs of `level` (rq/convert.rs:78-82): bytes per polynomial */
 int fhe_b200_poly_packed_bytes(const fhe_b200_params* p, uint32_t level, size_t* nbytes);
 /* the same for the polynomials of one batch -- use this one to size the host buffers of pack / unpack: a batch over

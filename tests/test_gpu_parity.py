@@ -430,7 +430,7 @@ def test_wide_golden_fixture(F):
 @pytest.mark.parametrize("env", [{"FHE_B200_SOLINAS_NTT": "1"}, {"FHE_B200_NO_SOLINAS": "1"}, {"FHE_B200_GENERIC_NTT": "1"},
                                  {"FHE_B200_CHUNK": "1"}, {"FHE_B200_ROWS_TLOG": "12", "FHE_B200_COLS_TLOG": "12"},
                                  {"FHE_B200_NTT": "tma"}, {"FHE_B200_NTT": "fast"},
-                                 {"FHE_B200_NTT": "tma", "FHE_B200_CHUNK": "1"}])
+                                 {"FHE_B200_NTT": "tma", "FHE_B200_CHUNK": "1"}, {"FHE_B200_SCALER": "classic"}])
 def test_alternate_code_paths(F, env):
     """the optional arithmetic / kernel variants (Solinas twiddle pairs, Barrett-only folds, generic tile NTT,
     one-ciphertext chunks, 4096-word NTT tiles) must be bit-identical too: rerun the set-A multiply + the 2^13 NTT test under each switch"""
@@ -441,7 +441,7 @@ def test_alternate_code_paths(F, env):
     out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
                           "test_mul_relin_against_oracle and 4096 or test_ntt_forward_backward and 13-2 or "
                           "test_ntt_forward_backward and 14-3 or test_ntt_forward_backward and 15-2 or "
-                          "test_golden_fixture or test_full_size_set_c or test_set_b_ntt_config"],
+                          "test_golden_fixture or test_full_size_set_c or test_set_b_ntt_config or test_scalers"],
                          cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
@@ -795,3 +795,61 @@ def test_set_b_ntt_config(oracle, F):
     ogk.exponent, ogk.ksk = 3, oracle.KeySwitchingKey.from_arrays(opar, gc[0], gc[1])
     R = F.GaloisKey.from_arrays(gpar, 3, gc[0], gc[1]).relinearize(A).to_host()
     assert (R[1] == ogk.relinearize(oracle.Ciphertext.from_array(opar, a[1], 0)).to_array()).all()
+
+
+def test_two_devices_one_process(oracle, F):
+    """One host process driving parameter sets on two devices (a Rust host holding one Arc<BfvParameters> per GPU):
+    kernels that need the opt-in shared-memory size (4096-word NTT tiles at N = 2^16, the TMA kernels at N = 2^15)
+    must get it on every device, the caller's current device is left alone, and both devices give the oracle's
+    words.  Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    torch.cuda.set_device(0)
+    rng = np.random.default_rng(31)
+    for logn, nmod in ((16, 1), (15, 2)):
+        n = 1 << logn
+        opar = oracle.BfvParameters(n, 786433, moduli_sizes=[62] * nmod)
+        ctx = opar.context_at_level(0)
+        x = _rand_rows(rng, ctx.moduli, (8, 2), n)
+        exp = x.copy()
+        for i, op in enumerate(ctx.ops):
+            op.forward(exp[0, 0, i])
+        for dev in (0, 1, 0):
+            gpar = F.BfvParameters(n, 786433, moduli=opar.moduli, device=dev)
+            ct = F.Ciphertext.from_host(gpar, x, repr=F.POWER_BASIS)
+            got = ct.into_ntt().to_host()
+            assert (got[0, 0] == exp[0, 0]).all(), "device %d" % dev
+            assert (ct.into_power_basis().to_host() == x).all()
+            assert torch.cuda.current_device() == 0, "the library changed the caller's current device"
+    # set A multiply on device 1 against the oracle
+    degree, t = 1 << 12, 1032193
+    opar = oracle.BfvParameters(degree, t, moduli_sizes=[62, 62])
+    gpar = F.BfvParameters(degree, t, moduli=opar.moduli, device=1)
+    sk = oracle.SecretKey(opar, rng)
+    ork = oracle.RelinearizationKey(sk, rng)
+    grk = F.RelinearizationKey.from_arrays(gpar, *ork.ksk.arrays())
+    ca, cb = sk.encrypt(rng.integers(0, t, degree), 0, rng), sk.encrypt(rng.integers(0, t, degree), 0, rng)
+    A = F.Ciphertext.from_host(gpar, ca.to_array()[None])
+    B = F.Ciphertext.from_host(gpar, cb.to_array()[None])
+    got = F.Multiplicator.default(grk).multiply(A, B).to_host()[0]
+    assert (got == oracle.Multiplicator.default(ork).multiply(ca, cb).to_array()).all()
+    assert torch.cuda.current_device() == 0
+
+
+def test_packed_mul_basis_batch(oracle, F):
+    """pack / unpack of a batch over the multiplication basis (L + E limbs): the host buffer is sized per batch
+    (fhe_b200_batch_packed_bytes), and the blobs decode back to the same words"""
+    opar, gpar, rng = make_pair(oracle, F, 64, 3, 1153, 5)
+    mp = opar.level(0).mul_params
+    K = len(mp.to.moduli)
+    y = np.zeros((2, 2, K, 64), np.uint64)
+    for i, q in enumerate(mp.to.moduli):
+        y[:, :, i, :] = rng.integers(0, q, size=(2, 2, 64), dtype=np.uint64)
+    Y = F.Ciphertext.from_host(gpar, y, mul_basis=True, repr=F.POWER_BASIS)
+    blobs = Y.to_packed()
+    assert blobs.shape[2] == sum((q - 1).bit_length() * 64 // 8 for q in mp.to.moduli)
+    for i, q in enumerate(mp.to.moduli):
+        off = sum((qq - 1).bit_length() * 8 for qq in mp.to.moduli[:i])
+        nb = (q - 1).bit_length()
+        assert oracle.transcode_from_bytes(bytes(blobs[1, 0, off:off + nb * 8]), nb)[:64] == [int(v) for v in y[1, 0, i]]
