@@ -745,6 +745,111 @@ __global__ void ksmac_kernel(KsMacArgs A) {
   A.out1[o] = a1.reduce(M);
 }
 
+
+// ------------------------------------------------------------------ key-switch MAC, persistent TMA-fed form
+// The same sums as ksmac_kernel for the digit-adjacent layout (inter [ct][limb][digit][N], keys [limb][digit][N]).
+// The inner product is HBM-bound (14 digit words streamed per pair of outputs) but the per-thread form was bound by
+// load latency (~3.1 TB/s of the 6.5 TB/s copy rate): here one elected thread streams every operand with TMA box
+// copies and the compute threads only read shared memory.
+//   work item = (limb j, 128-coefficient tile tau, ciphertext ct), ct innermost: the two key tiles of (j, tau)
+//   ({128, n_dig} boxes, 2 x n_dig KiB) are fetched once and stay in shared memory for every ciphertext of the CTA's
+//   range; the digit tile of each ciphertext ({128, n_dig} box: its n_dig rows are adjacent) arrives through a ring of
+//   KS_STAGES buffers, refilled as soon as the CTA has consumed it.
+constexpr int kKsTC = 128, kKsStages = 4;
+struct KsTmaArgs {
+  const u64 *base0, *base1;
+  u64 *out0, *out1;
+  u32 cts, n_dig, Lk, out_ct_rows, logn;
+  u32 items_total;   // Lk * (N / 128) * cts, item = (j * tiles + tau) * cts + ct
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+
+__global__ void __launch_bounds__(kKsTC) ksmac_tma_kernel(const __grid_constant__ CUtensorMap tm_t,
+                                                          const __grid_constant__ CUtensorMap tm_k0,
+                                                          const __grid_constant__ CUtensorMap tm_k1, const KsTmaArgs A) {
+  using namespace tma;
+  extern __shared__ __align__(128) u64 smem[];
+  constexpr u32 TC = kKsTC, S = kKsStages;
+  const u32 nd = A.n_dig;
+  const u32 box_bytes = nd * TC * 8;
+  u64* s_k0 = smem;                       // [n_dig][TC]
+  u64* s_k1 = s_k0 + (size_t)nd * TC;
+  u64* s_t = s_k1 + (size_t)nd * TC;      // [S][n_dig][TC]
+  u64* s_bar = s_t + (size_t)S * nd * TC; // S full barriers + 1 key barrier
+  const u32 bar_full = smem_u32(s_bar), bar_key = bar_full + 8 * S;
+  const u32 cc = threadIdx.x;
+  if (cc == 0) {
+    for (u32 s = 0; s < S; s++) mbar_init(bar_full + 8 * s, 1);
+    mbar_init(bar_key, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const u32 tiles = (1u << A.logn) / TC;
+  const u32 lo = (u32)(((u64)A.items_total * blockIdx.x) / gridDim.x);
+  const u32 hi = (u32)(((u64)A.items_total * (blockIdx.x + 1)) / gridDim.x);
+  const u32 n = hi - lo;
+  // item -> (jt, ct) walkers: `wl` for the loads thread 0 issues ahead, `w` for the item being computed
+  TileWalk wl, w;
+  wl.init(lo, A.cts);
+  w.init(lo, A.cts);
+  u32 loaded = 0;
+  auto load_next = [&]() {   // thread 0 only
+    const u32 s = loaded % S;
+    const u32 j = wl.jt / tiles, tau = wl.jt - j * tiles;
+    mbar_expect_tx(bar_full + 8 * s, box_bytes);
+    load_2d(smem_u32(s_t + (size_t)s * nd * TC), &tm_t, tau * TC, (wl.p * A.Lk + j) * nd, bar_full + 8 * s);
+    wl.next();
+    loaded++;
+  };
+  if (cc == 0)
+    while (loaded < n && loaded < S) load_next();
+
+  u32 cur_jt = 0xffffffffu, key_phase = 0;
+  const LimbDev* Mp = A.limbs;
+  for (u32 i = 0; i < n; i++) {
+    if (w.jt != cur_jt) {
+      // new (limb, tile): its two key tiles replace the previous ones (every thread has finished with those: the
+      // item loop ends with a CTA barrier)
+      cur_jt = w.jt;
+      const u32 j = cur_jt / tiles, tau = cur_jt - j * tiles;
+      Mp = A.limbs + A.ids[j];
+      if (cc == 0) {
+        mbar_expect_tx(bar_key, 2 * box_bytes);
+        load_2d(smem_u32(s_k0), &tm_k0, tau * TC, j * nd, bar_key);
+        load_2d(smem_u32(s_k1), &tm_k1, tau * TC, j * nd, bar_key);
+      }
+      mbar_wait(bar_key, key_phase);
+      key_phase ^= 1;
+    }
+    const u32 j = cur_jt / tiles, tau = cur_jt - j * tiles;
+    const u32 s = i % S;
+    const size_t o = (((size_t)w.p * A.out_ct_rows + j) << A.logn) + tau * TC + cc;
+    u64 b0 = 0, b1 = 0;
+    if (A.base0) b0 = A.base0[o];
+    if (A.base1) b1 = A.base1[o];
+    mbar_wait(bar_full + 8 * s, (i / S) & 1);
+    const u64* t = s_t + (size_t)s * nd * TC + cc;
+    Acc192 a0, a1;
+    a0.clear();
+    a1.clear();
+#pragma unroll 2
+    for (u32 d = 0; d < nd; d++) {
+      const u64 td = t[d * TC];
+      a0.mac(td, s_k0[d * TC + cc]);
+      a1.mac(td, s_k1[d * TC + cc]);
+    }
+    a0.add64(b0);
+    a1.add64(b1);
+    A.out0[o] = a0.reduce(*Mp);
+    A.out1[o] = a1.reduce(*Mp);
+    __syncthreads();                       // stage s (and, before a key change, the key tiles) are free again
+    if (cc == 0 && loaded < n) load_next();
+    w.next();
+  }
+}
+
 // base-2^log_base digits of a single-limb power-basis polynomial (key_switching_key.rs:339-345):
 // out[poly][d][:] = (in[poly][:] >> (d * log_base)) & (2^log_base - 1)
 __global__ void decompose_kernel(const u64* in, u64* out, size_t n_words, u32 n_dig, u32 log_base, u32 logn) {
@@ -1016,14 +1121,45 @@ void launch_scale(const ScalerDev& S, const LimbDev* limbs, const u64* in, u64* 
 void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* base0, const u64* base1, u64* out0,
                   u64* out1, u32 cts, u32 n_dig, u32 Lk, u32 out_ct_rows, const RowIds& ids, const LimbDev* limbs,
                   u32 logn, cudaStream_t st, bool adjacent) {
+  size_t total = ((size_t)cts * Lk) << logn;
+  if (!total) return;
+  static const bool classic = [] { const char* e = getenv("FHE_B200_KSMAC"); return e && !strcmp(e, "classic"); }();
+  const size_t smem_tma = ((size_t)(2 + kKsStages) * n_dig * kKsTC + kKsStages + 1) * sizeof(u64);
+  if (adjacent && !classic && scale_encoder() && logn >= 7 && n_dig <= 256 && smem_tma <= 200 * 1024 &&
+      !((reinterpret_cast<uintptr_t>(inter) | reinterpret_cast<uintptr_t>(k0) | reinterpret_cast<uintptr_t>(k1)) & 127) &&
+      (u64)cts * Lk * n_dig < (1ull << 31)) {
+    auto map = [&](const u64* base, u64 rows, CUtensorMap* m) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)1 << logn, rows};
+      const cuuint64_t gstride[1] = {(cuuint64_t)8 << logn};
+      const cuuint32_t box[2] = {(cuuint32_t)kKsTC, n_dig};
+      const cuuint32_t es[2] = {1, 1};
+      return scale_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)base, gdim, gstride, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    CUtensorMap mt, m0, m1;
+    if (map(inter, (u64)cts * Lk * n_dig, &mt) && map(k0, (u64)Lk * n_dig, &m0) && map(k1, (u64)Lk * n_dig, &m1)) {
+      KsTmaArgs T;
+      T.base0 = base0; T.base1 = base1; T.out0 = out0; T.out1 = out1;
+      T.cts = cts; T.n_dig = n_dig; T.Lk = Lk; T.out_ct_rows = out_ct_rows; T.logn = logn;
+      T.items_total = Lk * ((1u << logn) / kKsTC) * cts;
+      T.limbs = limbs;
+      copy_ids(T.ids, ids);
+      ensure_dynamic_smem((const void*)ksmac_tma_kernel, smem_tma);
+      int per_sm = 0;
+      FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)ksmac_tma_kernel, kKsTC, smem_tma));
+      const u32 grid = (u32)std::min<u64>(T.items_total, (u64)scale_sm_count() * std::max(per_sm, 1));
+      ksmac_tma_kernel<<<grid, kKsTC, smem_tma, st>>>(mt, m0, m1, T);
+      g_launches++;
+      return;
+    }
+  }
   KsMacArgs A;
   A.adjacent = adjacent ? 1 : 0;
   A.inter = inter; A.k0 = k0; A.k1 = k1; A.base0 = base0; A.base1 = base1; A.out0 = out0; A.out1 = out1;
   A.cts = cts; A.n_dig = n_dig; A.Lk = Lk; A.out_ct_rows = out_ct_rows; A.logn = logn;
   A.limbs = limbs;
   copy_ids(A.ids, ids);
-  size_t total = ((size_t)cts * Lk) << logn;
-  if (!total) return;
   ksmac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
   g_launches++;
 }
