@@ -268,10 +268,10 @@ __device__ __forceinline__ U256 u256_mul_128(u128 v, u64 tlo, u64 thi) {
 constexpr int kScaleTC = 128;
 
 // sum_i r_i * omega_{j0+k, i} for the G (<= 4) output limbs of one group
-template <int G>
+template <int G, int UNR = 2>
 __device__ __forceinline__ void scale_mac_group(Acc192 (&acc)[4], const u64* r_col, const ulonglong2* om, u32 nf,
                                                 u32 om_stride) {
-#pragma unroll 2
+#pragma unroll UNR
   for (u32 i = 0; i < nf; i++) {
     const u64 r = r_col[i * kScaleTC];
     const ulonglong2 o0 = om[(size_t)i * om_stride];
@@ -448,7 +448,7 @@ struct ScaleTmaArgs {
   u32 tiles_total;   // polys * N / 128
 };
 
-template <bool IS_ONE>
+template <bool IS_ONE, int UNR>
 __global__ void __launch_bounds__(kScaleTC) scale_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const ScaleTmaArgs A) {
   using namespace tma;
   extern __shared__ __align__(128) u64 smem[];
@@ -580,10 +580,10 @@ __global__ void __launch_bounds__(kScaleTC) scale_tma_kernel(const __grid_consta
       const ulonglong2* om = reinterpret_cast<const ulonglong2*>(s_omega + j0);
       const u32 g = min(4u, n_out - j0);
       switch (g) {
-        case 4: scale_mac_group<4>(acc, s_r + cc, om, nf, n_out4 / 2); break;
-        case 3: scale_mac_group<3>(acc, s_r + cc, om, nf, n_out4 / 2); break;
-        case 2: scale_mac_group<2>(acc, s_r + cc, om, nf, n_out4 / 2); break;
-        default: scale_mac_group<1>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+        case 4: scale_mac_group<4, UNR>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+        case 3: scale_mac_group<3, UNR>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+        case 2: scale_mac_group<2, UNR>(acc, s_r + cc, om, nf, n_out4 / 2); break;
+        default: scale_mac_group<1, UNR>(acc, s_r + cc, om, nf, n_out4 / 2); break;
       }
       if (j0 + 4 >= n_out) {
         // the tile has been read for the last time: fetch the next one while the last epilogue runs
@@ -755,7 +755,7 @@ __global__ void ksmac_kernel(KsMacArgs A) {
 //   ({128, n_dig} boxes, 2 x n_dig KiB) are fetched once and stay in shared memory for every ciphertext of the CTA's
 //   range; the digit tile of each ciphertext ({128, n_dig} box: its n_dig rows are adjacent) arrives through a ring of
 //   KS_STAGES buffers, refilled as soon as the CTA has consumed it.
-constexpr int kKsTC = 128, kKsStages = 4;
+constexpr int kKsTC = 128;
 struct KsTmaArgs {
   const u64 *base0, *base1;
   u64 *out0, *out1;
@@ -765,12 +765,13 @@ struct KsTmaArgs {
   unsigned short ids[kMaxPos];
 };
 
+template <int KS_STAGES>
 __global__ void __launch_bounds__(kKsTC) ksmac_tma_kernel(const __grid_constant__ CUtensorMap tm_t,
                                                           const __grid_constant__ CUtensorMap tm_k0,
                                                           const __grid_constant__ CUtensorMap tm_k1, const KsTmaArgs A) {
   using namespace tma;
   extern __shared__ __align__(128) u64 smem[];
-  constexpr u32 TC = kKsTC, S = kKsStages;
+  constexpr u32 TC = kKsTC, S = KS_STAGES;
   const u32 nd = A.n_dig;
   const u32 box_bytes = nd * TC * 8;
   u64* s_k0 = smem;                       // [n_dig][TC]
@@ -1088,8 +1089,14 @@ static bool launch_scale_tma(const ScalerDev& S, const LimbDev* limbs, const std
     FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kScaleTC, smem));
     return (u32)std::min<u64>(A.tiles_total, (u64)scale_sm_count() * std::max(per_sm, 1));
   };
-  if (S.is_one) scale_tma_kernel<true><<<resident((const void*)scale_tma_kernel<true>), kScaleTC, smem, st>>>(tm, A);
-  else scale_tma_kernel<false><<<resident((const void*)scale_tma_kernel<false>), kScaleTC, smem, st>>>(tm, A);
+  static const int unr = [] { const char* e = getenv("FHE_B200_SCALE_UNROLL"); return e ? atoi(e) : 2; }();
+  if (unr == 4) {
+    if (S.is_one) scale_tma_kernel<true, 4><<<resident((const void*)scale_tma_kernel<true, 4>), kScaleTC, smem, st>>>(tm, A);
+    else scale_tma_kernel<false, 4><<<resident((const void*)scale_tma_kernel<false, 4>), kScaleTC, smem, st>>>(tm, A);
+  } else {
+    if (S.is_one) scale_tma_kernel<true, 2><<<resident((const void*)scale_tma_kernel<true, 2>), kScaleTC, smem, st>>>(tm, A);
+    else scale_tma_kernel<false, 2><<<resident((const void*)scale_tma_kernel<false, 2>), kScaleTC, smem, st>>>(tm, A);
+  }
   g_launches++;
   return true;
 }
@@ -1124,7 +1131,10 @@ void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* bas
   size_t total = ((size_t)cts * Lk) << logn;
   if (!total) return;
   static const bool classic = [] { const char* e = getenv("FHE_B200_KSMAC"); return e && !strcmp(e, "classic"); }();
-  const size_t smem_tma = ((size_t)(2 + kKsStages) * n_dig * kKsTC + kKsStages + 1) * sizeof(u64);
+  // ring depth: 2 buffers -> 4 resident CTAs per SM at set C measured best (4333 products/s; 3 buffers / 3 CTAs 4314,
+  // 4 buffers / 2 CTAs 4279): the kernel needs warps more than prefetch depth.  FHE_B200_KS_STAGES = 2 | 3 | 4.
+  static const int stages = [] { const char* e = getenv("FHE_B200_KS_STAGES"); int v = e ? atoi(e) : 2; return v < 2 ? 2 : v > 4 ? 4 : v; }();
+  const size_t smem_tma = ((size_t)(2 + stages) * n_dig * kKsTC + stages + 1) * sizeof(u64);
   if (adjacent && !classic && scale_encoder() && logn >= 7 && n_dig <= 256 && smem_tma <= 200 * 1024 &&
       !((reinterpret_cast<uintptr_t>(inter) | reinterpret_cast<uintptr_t>(k0) | reinterpret_cast<uintptr_t>(k1)) & 127) &&
       (u64)cts * Lk * n_dig < (1ull << 31)) {
@@ -1145,11 +1155,16 @@ void launch_ksmac(const u64* inter, const u64* k0, const u64* k1, const u64* bas
       T.items_total = Lk * ((1u << logn) / kKsTC) * cts;
       T.limbs = limbs;
       copy_ids(T.ids, ids);
-      ensure_dynamic_smem((const void*)ksmac_tma_kernel, smem_tma);
-      int per_sm = 0;
-      FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)ksmac_tma_kernel, kKsTC, smem_tma));
-      const u32 grid = (u32)std::min<u64>(T.items_total, (u64)scale_sm_count() * std::max(per_sm, 1));
-      ksmac_tma_kernel<<<grid, kKsTC, smem_tma, st>>>(mt, m0, m1, T);
+      auto go = [&](auto kern) {
+        ensure_dynamic_smem((const void*)kern, smem_tma);
+        int per_sm = 0;
+        FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, kKsTC, smem_tma));
+        const u32 grid = (u32)std::min<u64>(T.items_total, (u64)scale_sm_count() * std::max(per_sm, 1));
+        kern<<<grid, kKsTC, smem_tma, st>>>(mt, m0, m1, T);
+      };
+      if (stages == 2) go(ksmac_tma_kernel<2>);
+      else if (stages == 3) go(ksmac_tma_kernel<3>);
+      else go(ksmac_tma_kernel<4>);
       g_launches++;
       return;
     }

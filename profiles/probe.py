@@ -27,7 +27,16 @@ par = F.BfvParameters(DEGREE, PLAINTEXT, moduli_sizes=[62] * N_MODULI, device=0)
 moduli = par.moduli()
 A = F.Ciphertext(par, count, 2)
 fill_uniform(torch, A, moduli, 1)
-if what == "ntt":
+if what == "rotate":  # BASELINE config 4: GaloisKey rotate (exponent 3)
+    rng = np.random.default_rng(9)
+    gc = np.zeros((2, N_MODULI, N_MODULI, DEGREE), np.uint64)
+    for i, q in enumerate(moduli):
+        gc[:, :, i, :] = rng.integers(0, q, size=(2, N_MODULI, DEGREE), dtype=np.uint64)
+    gk = F.GaloisKey.from_arrays(par, 3, gc[0], gc[1])
+    for _ in range(2):
+        out = gk.relinearize(A)
+    out.sync()
+elif what == "ntt":
     for _ in range(2):
         A.into_power_basis()
         A.into_ntt()

@@ -19,9 +19,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "..", "fhe_rs_b200", "libfhe_b200.so")
 
-DEFAULT = ["ntt_tma", "ntt_fast_kernelILi9ELb1ELb0ELi11", "ntt_fast_kernelILi9ELb1ELb1ELi11",
-           "ntt_fast_kernelILi6ELb0ELb0ELi10", "ntt_fast_kernelILi6ELb0ELb1ELi10", "scale_kernel", "ksmac",
-           "tensor_kernel"]
+DEFAULT = ["ntt_tma_cols_kernelILi9", "ntt_tma_cols_kernelILi8", "ntt_tma_rows_kernel", "scale_tma_kernel",
+           "ksmac_tma_kernel", "tensor_kernel", "ntt_fast_kernelILi9ELb1ELb0ELi11", "ntt_fast_kernelILi6ELb0ELb0ELi10",
+           "scale_kernel", "12ksmac_kernel"]
 
 
 def classify(op: str) -> str:
