@@ -452,10 +452,12 @@ void mul_core(const fhe_b200_params* par, const LevelData& lv, const u64* a, con
   // rq/scaler.rs:97-115: forward NTT of the new rows
   launch_ntt(X_l, X_l, cts * 2 * E, ext_ids, par->d_limbs, logn, false, 1, false, st);
   launch_ntt(X_r, X_r, cts * 2 * E, ext_ids, par->d_limbs, logn, false, 1, false, st);
-  // mul.rs:198-201
-  launch_tensor(a, b, X_l, X_r, T, cts, L, L, L, K, lv.mul_ids, par->d_limbs, logn, st);
-  // mul.rs:204-206: scale down by t/Q (backward NTT of K rows, exact scaling K -> L)
-  launch_ntt(T, T, cts * 3 * K, lv.mul_ids, par->d_limbs, logn, true, 1, false, st);
+  // mul.rs:198-201 tensor product, then mul.rs:204-206 scale down by t/Q (backward NTT of the 3K rows, exact scaling
+  // K -> L); product and first inverse pass run as one kernel where the TMA kernels serve the shape
+  if (!launch_tensor_inverse_ntt(a, b, X_l, X_r, T, cts, L, K, lv.mul_ids, par->d_limbs, logn, st)) {
+    launch_tensor(a, b, X_l, X_r, T, cts, L, L, L, K, lv.mul_ids, par->d_limbs, logn, st);
+    launch_ntt(T, T, cts * 3 * K, lv.mul_ids, par->d_limbs, logn, true, 1, false, st);
+  }
   launch_scale(lv.down.dev, par->d_limbs, T, out0, out1, cts * 3, L, 0, L, split, logn, st);
 }
 

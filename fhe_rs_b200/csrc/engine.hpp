@@ -40,6 +40,12 @@ void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const Li
                 bool inverse, u32 in_div, bool reduce_on_load, cudaStream_t st, bool lazy_out = false,
                 bool digit_adjacent = false, u32 n_dig = 1);
 
+// Tensor product of two 2-part ciphertexts (as launch_tensor with nca == ncb == L) fused with the inverse transform of
+// its 3K output rows: T [ct][3][K][N] receives the POWER-BASIS products.  Returns false when the TMA kernels do not
+// serve the shape (the caller then runs launch_tensor + launch_ntt).
+bool launch_tensor_inverse_ntt(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* T, u32 cts, u32 L, u32 K,
+                               const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st);
+
 // ---- element-wise (kernels.cu)
 enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2 };
 void launch_ew(EwOp op, u64* a, const u64* b, size_t n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,

@@ -270,6 +270,49 @@ bool launch_ntt_tma(const u64* in, u64* out, u32 n_rows, const RowIds& ids, cons
   return true;
 }
 
+// tensor product + first inverse pass fused (ntt_tma_tensor_rows_kernel), then the inverse cols pass in place on T
+template <int STAGES, int MINB>
+void run_tensor_rows(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mxa, const CUtensorMap& mxb,
+                     const CUtensorMap& mo, TensorRowsArgs A, cudaStream_t st) {
+  using Cfg = TensorRowsCfg<kRowsRlog, STAGES>;
+  auto k = ntt_tma_tensor_rows_kernel<kRowsRlog, STAGES, MINB>;
+  ensure_dynamic_smem((const void*)k, Cfg::SMEM);
+  const u32 grid = std::min<u64>(A.items_total, (u64)sm_count() * MINB);
+  k<<<grid, Cfg::NT + 32, Cfg::SMEM, st>>>(ma, mb, mxa, mxb, mo, A);
+  g_launches++;
+}
+
+// tensor product + first inverse pass fused (ntt_tma_tensor_rows_kernel), then the inverse cols pass in place on T
+bool launch_tensor_intt_tma(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* T, u32 cts, u32 L, u32 K,
+                            const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st) {
+  constexpr u32 R = 1u << kRowsRlog;
+  const u32 E = K - L;
+  try {
+    const CUtensorMap ma = rows_map(a, (u64)cts * 2 * L, logn, 4 * R), mb = rows_map(b, (u64)cts * 2 * L, logn, 4 * R);
+    const CUtensorMap mxa = rows_map(xa, (u64)cts * 2 * E, logn, 4 * R), mxb = rows_map(xb, (u64)cts * 2 * E, logn, 4 * R);
+    const CUtensorMap mo = rows_map(T, (u64)cts * 3 * K, logn, 4 * R);
+    TensorRowsArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.limbs = limbs; A.cts = cts; A.L = L; A.K = K; A.logn = logn;
+    A.tiles_per_row = (1u << (logn - 6)) / R;
+    A.items_total = K * A.tiles_per_row * cts;
+    for (int i = 0; i < kMaxPos; i++) A.ids[i] = mul_ids.ids[i];
+    static const int v = tma_variant("FHE_B200_TENSOR_V", 22);   // ring depth x CTAs per SM
+    if (v == 13) run_tensor_rows<1, 3>(ma, mb, mxa, mxb, mo, A, st);
+    else if (v == 14) run_tensor_rows<1, 4>(ma, mb, mxa, mxb, mo, A, st);
+    else run_tensor_rows<2, 2>(ma, mb, mxa, mxb, mo, A, st);
+    // second pass of the inverse transform of the 3K product rows, in place
+    NttTmaArgs C;
+    std::memset(&C, 0, sizeof(C));
+    C.limbs = limbs; C.n_polys = cts * 3; C.lpp = K; C.logn = logn; C.n_dig = 1;
+    for (int i = 0; i < kMaxPos; i++) C.ids[i] = mul_ids.ids[i];
+    run_tma_cols_for<true>(T, (u64)cts * 3 * K, T, (u64)cts * 3 * K, C, st);
+  } catch (const TmaFail&) {
+    return false;
+  }
+  return true;
+}
+
 int tma_mode() {
   static const int mode = [] {
     const char* e = getenv("FHE_B200_NTT");
@@ -292,6 +335,16 @@ bool ntt_uses_tma(u32 n_rows, const RowIds& ids, u32 logn, u32 in_div, const u64
   if (n_rows % lpp != 0 || (in_div != 1 && in_div != lpp)) return false;
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 127) return false;
   return tma_mode() == 2 || n_rows / lpp >= 8;
+}
+
+bool launch_tensor_inverse_ntt(const u64* a, const u64* b, const u64* xa, const u64* xb, u64* T, u32 cts, u32 L, u32 K,
+                               const RowIds& mul_ids, const LimbDev* limbs, u32 logn, cudaStream_t st) {
+  static const bool off = getenv("FHE_B200_NO_TENSOR_FUSION") != nullptr;
+  if (off || K <= L || !ntt_uses_tma(cts * 3 * K, mul_ids, logn, 1, T, T)) return false;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(xa) |
+       reinterpret_cast<uintptr_t>(xb)) & 127)
+    return false;
+  return launch_tensor_intt_tma(a, b, xa, xb, T, cts, L, K, mul_ids, limbs, logn, st);
 }
 
 void launch_ntt(const u64* in, u64* out, u32 n_rows, const RowIds& ids, const LimbDev* limbs, u32 logn,

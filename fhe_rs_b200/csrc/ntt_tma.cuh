@@ -406,6 +406,220 @@ __global__ void __launch_bounds__(RowsCfg<RLOG, STAGES>::NT + 32, MINB)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor + inverse rows
+// The tensor product of two 2-part ciphertexts over the multiplication basis (c0 = a0*b0, c1 = a0*b1 + a1*b0,
+// c2 = a1*b1; bfv/ops/mul.rs:198-201, Modulus::mul_vec zq/mod.rs:332) fused with the FIRST pass of the inverse
+// transform that always follows it (mul.rs:204: the scaler takes power-basis input).  The product is point-wise and the
+// inverse rows pass starts from the same 1024-word tile of every row, so one work item = (limb j, tile tau,
+// ciphertext ct): four source tiles in (a0, a1, b0, b1 -- from the ciphertexts themselves for the common-prefix
+// limbs, from the extended rows otherwise), three transformed tiles out.  The 3K product rows never travel to HBM
+// and back between the two steps, and the stand-alone tensor kernel disappears from the path.
+struct TensorRowsArgs {
+  const LimbDev* limbs;
+  u32 cts, L, K, logn;
+  u32 tiles_per_row;
+  u32 items_total;     // K * tiles_per_row * cts; item = (j*tiles_per_row + tau)*cts + ct
+  unsigned short ids[kMaxPos];   // multiplication-basis position -> limb
+};
+
+template <int RLOG, int STAGES>
+struct TensorRowsCfg {
+  static constexpr u32 R = 1u << RLOG;
+  static constexpr u32 NT = 8 * R;
+  static constexpr u32 TILE_BYTES = 512 * R;
+  static constexpr u32 STAGE_BYTES = 4 * TILE_BYTES;
+  static constexpr u32 TW_PAIRS = 63 * R;
+  static constexpr u32 SMEM = STAGES * STAGE_BYTES + TW_PAIRS * 16 + 2 * STAGES * 8 + 1024;
+};
+
+template <int RLOG, int STAGES, int MINB>
+__global__ void __launch_bounds__(TensorRowsCfg<RLOG, STAGES>::NT + 32, MINB)
+    ntt_tma_tensor_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                               const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
+                               const __grid_constant__ CUtensorMap tm_out, const TensorRowsArgs A) {
+  using namespace tma;
+  using Cfg = TensorRowsCfg<RLOG, STAGES>;
+  constexpr u32 R = Cfg::R, NT = Cfg::NT, TILE_BYTES = Cfg::TILE_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+  extern __shared__ unsigned char smem_raw[];
+  const u32 base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const u32 tw_base = base + STAGES * STAGE_BYTES;
+  const u32 bar_full = tw_base + Cfg::TW_PAIRS * 16;
+  const u32 bar_done = bar_full + STAGES * 8;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_done + 8 * s, NT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const u32 lo = (u32)(((u64)A.items_total * blockIdx.x) / gridDim.x);
+  const u32 hi = (u32)(((u64)A.items_total * (blockIdx.x + 1)) / gridDim.x);
+  const u32 n = hi - lo;
+  const u32 box_rows_per_row = (1u << A.logn) >> 4;
+  const u32 E = A.K - A.L;
+
+  if (threadIdx.x >= NT) {
+    if (threadIdx.x != NT) return;
+    prefetch_map(&tm_a);
+    prefetch_map(&tm_b);
+    prefetch_map(&tm_xa);
+    prefetch_map(&tm_xb);
+    prefetch_map(&tm_out);
+    TileWalk wl, ws;
+    wl.init(lo, A.cts);
+    ws.init(lo, A.cts);
+    u32 loaded = 0;
+    auto load_next = [&]() {
+      const u32 s = loaded % STAGES;
+      const u32 j = wl.jt / A.tiles_per_row, tau = wl.jt - j * A.tiles_per_row;
+      const u32 ct = wl.p;
+      const bool pre = j < A.L;                       // common-prefix limb: the operands themselves
+      const u32 rows = pre ? A.L : E, jj = pre ? j : j - A.L;
+      const CUtensorMap* ma = pre ? &tm_a : &tm_xa;
+      const CUtensorMap* mb = pre ? &tm_b : &tm_xb;
+      const u32 r0 = ((ct * 2) * rows + jj) * box_rows_per_row + tau * (4 * R);
+      const u32 r1 = ((ct * 2 + 1) * rows + jj) * box_rows_per_row + tau * (4 * R);
+      const u32 dst = base + s * STAGE_BYTES, bar = bar_full + 8 * s;
+      mbar_expect_tx(bar, STAGE_BYTES);
+      load_2d(dst, ma, 0, r0, bar);
+      load_2d(dst + TILE_BYTES, ma, 0, r1, bar);
+      load_2d(dst + 2 * TILE_BYTES, mb, 0, r0, bar);
+      load_2d(dst + 3 * TILE_BYTES, mb, 0, r1, bar);
+      wl.next();
+      loaded++;
+    };
+    while (loaded < n && loaded < (u32)STAGES) load_next();
+    for (u32 i = 0; i < n; i++) {
+      const u32 s = i % STAGES;
+      mbar_wait(bar_done + 8 * s, (i / STAGES) & 1);
+      const u32 j = ws.jt / A.tiles_per_row, tau = ws.jt - j * A.tiles_per_row;
+      const u32 ct = ws.p;
+      const u32 src = base + s * STAGE_BYTES;
+      // transformed c0 sits in the a0 buffer, c1 in the b0 buffer, c2 in the a1 buffer
+      store_2d(&tm_out, 0, ((ct * 3 + 0) * A.K + j) * box_rows_per_row + tau * (4 * R), src);
+      store_2d(&tm_out, 0, ((ct * 3 + 1) * A.K + j) * box_rows_per_row + tau * (4 * R), src + 2 * TILE_BYTES);
+      store_2d(&tm_out, 0, ((ct * 3 + 2) * A.K + j) * box_rows_per_row + tau * (4 * R), src + TILE_BYTES);
+      bulk_commit();
+      ws.next();
+      if (loaded < n) {
+        bulk_wait_read<0>();
+        load_next();
+      }
+    }
+    bulk_wait_all();
+    return;
+  }
+
+  const u32 tid = threadIdx.x;
+  const u32 x = tid & 7, b = tid >> 3;
+  u32 off0[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const u32 i = 64 * b + x + 8 * e;
+    off0[e] = ((i >> 4) << 7) | ((((i >> 1) & 7) ^ ((i >> 4) & 7)) << 4) | ((i & 1) << 3);
+  }
+  u32 off1[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const u32 i = 64 * b + 8 * x + 2 * k;
+    off1[k] = ((i >> 4) << 7) | ((((i >> 1) & 7) ^ ((i >> 4) & 7)) << 4);
+  }
+  const u32 tw0 = tw_base + 16 * (b);
+  const u32 tw1 = tw_base + 16 * (R * 1 + (b << 1));
+  const u32 tw2 = tw_base + 16 * (R * 3 + (b << 2));
+  const u32 tw3 = tw_base + 16 * (R * 7 + tid);
+  const u32 tw4 = tw_base + 16 * (R * 15 + tid);
+  const u32 tw5 = tw_base + 16 * (R * 31 + tid);
+
+  TileWalk w;
+  w.init(lo, A.cts);
+  bool fresh = true;
+  LimbDev M = A.limbs[0];
+  const u32 logn1 = A.logn - 6;
+  for (u32 i = 0; i < n; i++) {
+    if (fresh) {
+      const u32 j = w.jt / A.tiles_per_row, tau = w.jt - j * A.tiles_per_row;
+      M = A.limbs[A.ids[j]];
+      const ulonglong2* tab = M.zi;
+      const u32 row0 = tau * R;
+      if (i) consumer_sync<NT>();
+#pragma unroll
+      for (int tl = 0; tl < 6; tl++) {
+        const u32 s = logn1 + tl;
+        const u32 g0 = ((1u << A.logn) - (2u << s)) + (row0 << tl);
+        for (u32 k = tid; k < (R << tl); k += NT) {
+          const ulonglong2 v = __ldg(tab + g0 + k);
+          const u32 dst = tl < 3 ? k : (k & ((1u << (tl >= 3 ? tl - 3 : 0)) - 1)) * (8 * R) + (k >> (tl >= 3 ? tl - 3 : 0));
+          sts128(tw_base + 16 * (R * ((1u << tl) - 1) + dst), v.x, v.y);
+        }
+      }
+      consumer_sync<NT>();
+    }
+    const u64 p = M.p, p2 = M.p2;
+    const u32 s = i % STAGES;
+    const u32 buf = base + s * STAGE_BYTES;
+    mbar_wait(bar_full + 8 * s, (i / STAGES) & 1);
+    // point-wise products of this thread's 8 consecutive positions of the tile
+    u64 v0[8], v1[8], v2[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const ulonglong2 a0 = lds128(buf + off1[k]), a1 = lds128(buf + TILE_BYTES + off1[k]);
+      const ulonglong2 b0 = lds128(buf + 2 * TILE_BYTES + off1[k]), b1 = lds128(buf + 3 * TILE_BYTES + off1[k]);
+      v0[2 * k] = mulmod_limb(a0.x, b0.x, M);
+      v0[2 * k + 1] = mulmod_limb(a0.y, b0.y, M);
+      v2[2 * k] = mulmod_limb(a1.x, b1.x, M);
+      v2[2 * k + 1] = mulmod_limb(a1.y, b1.y, M);
+      Acc192 sx, sy;                               // a0*b1 + a1*b0 < 2^125, one reduction
+      sx.clear();
+      sy.clear();
+      sx.mac(a0.x, b1.x);
+      sx.mac(a1.x, b0.x);
+      sy.mac(a0.y, b1.y);
+      sy.mac(a1.y, b0.y);
+      v1[2 * k] = sx.reduce(M);
+      v1[2 * k + 1] = sy.reduce(M);
+    }
+    // inverse round 1 (strides 1, 2, 4) of the three product tiles, deposited over the consumed operand tiles
+    ulonglong2 tw[7];
+    tw[0] = lds128(tw3);
+    tw[1] = lds128(tw4);
+    tw[2] = lds128(tw4 + 16 * 8 * R);
+#pragma unroll
+    for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw5 + 16 * 8 * R * m);
+    inv_stages<3>(v0, tw, p, p2, false, M);
+    inv_stages<3>(v1, tw, p, p2, false, M);
+    inv_stages<3>(v2, tw, p, p2, false, M);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      sts128(buf + off1[k], v0[2 * k], v0[2 * k + 1]);                     // c0 -> a0 buffer
+      sts128(buf + 2 * TILE_BYTES + off1[k], v1[2 * k], v1[2 * k + 1]);    // c1 -> b0 buffer
+      sts128(buf + TILE_BYTES + off1[k], v2[2 * k], v2[2 * k + 1]);        // c2 -> a1 buffer
+    }
+    consumer_sync<NT>();
+    // inverse round 0 (strides 8, 16, 32) of each product tile
+    tw[0] = lds128(tw0);
+    tw[1] = lds128(tw1);
+    tw[2] = lds128(tw1 + 16);
+#pragma unroll
+    for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw2 + 16 * m);
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const u32 tb = buf + t * TILE_BYTES;
+#pragma unroll
+      for (int e = 0; e < 8; e++) v0[e] = lds64(tb + off0[e]);
+      inv_stages<3>(v0, tw, p, p2, false, M);
+#pragma unroll
+      for (int e = 0; e < 8; e++) sts64(tb + off0[e], v0[e]);
+    }
+    fence_proxy_async();
+    mbar_arrive(bar_done + 8 * s);
+    fresh = w.next();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ cols pass
 // The log2(N1) large-stride stages on tiles of all N1 = 2^LOGP points x 16 adjacent columns (128-byte segments at
 // stride 512 bytes).  2^LOGP consumer threads + one producer warp; radix-8 rounds in place, 16 / 8 words per thread
