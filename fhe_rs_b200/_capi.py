@@ -42,6 +42,8 @@ SYMBOLS = {
     "fhe_b200_batch_download": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "fhe_b200_batch_download_async": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "fhe_b200_batch_copy": (_i, [_vp, _vp, _vp]),
+    "fhe_b200_host_alloc": (_i, [C.c_size_t, _i, _pp]),
+    "fhe_b200_host_free": (_i, [_vp]),
     "fhe_b200_batch_device_ptr": (_i, [_vp, _pp, C.POINTER(C.c_size_t)]),
     "fhe_b200_ksk_upload": (_i, [_vp, _u32, _u32, _vp, _vp, _u32, _pp]),
     "fhe_b200_ksk_free": (_i, [_vp]),

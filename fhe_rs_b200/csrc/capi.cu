@@ -308,6 +308,22 @@ struct DeviceGuard {
   DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
+// the same for the release paths: never throws, puts the caller's device back
+struct ScopedDevice {
+  int prev = -1;
+  explicit ScopedDevice(int device) {
+    if (device < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev == device) prev = -1;
+    else cudaSetDevice(device);
+    cudaGetLastError();
+  }
+  ~ScopedDevice() {
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+  }
+};
+
 // owning device pointer for the construction of handles (released on commit)
 struct DevPtr {
   void* p = nullptr;
@@ -708,9 +724,11 @@ int fhe_b200_batch_alloc_mul_basis(const fhe_b200_params* p, uint32_t count, uin
 }
 int fhe_b200_batch_free(fhe_b200_batch* b) {
   if (!b) return FHE_B200_OK;
-  if (b->par->device >= 0) cudaSetDevice(b->par->device);
-  cudaFree(b->d);
-  cudaGetLastError();
+  {
+    ScopedDevice g(b->par->device);
+    cudaFree(b->d);
+    cudaGetLastError();
+  }
   params_release(b->par);
   delete b;
   return FHE_B200_OK;
@@ -762,6 +780,19 @@ int fhe_b200_batch_copy(fhe_b200_batch* dst, const fhe_b200_batch* src, void* st
   FHE_CUDA(cudaMemcpyAsync(dst->d, src->d, src->words_per_ct() * src->count * sizeof(u64), cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));
   dst->repr = src->repr;
+  API_END
+}
+int fhe_b200_host_alloc(size_t bytes, int write_combined, void** out) {
+  API_BEGIN
+  REQUIRE(out && bytes, FHE_B200_INVALID_ARGUMENT, "null argument");
+  void* p = nullptr;
+  FHE_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  *out = p;
+  API_END
+}
+int fhe_b200_host_free(void* p) {
+  API_BEGIN
+  if (p) FHE_CUDA(cudaFreeHost(p));
   API_END
 }
 int fhe_b200_batch_device_ptr(const fhe_b200_batch* b, uint64_t** dptr, size_t* n_words) {
@@ -816,10 +847,12 @@ int fhe_b200_ksk_upload(const fhe_b200_params* p, uint32_t ciphertext_level, uin
 }
 int fhe_b200_ksk_free(fhe_b200_ksk* k) {
   if (!k) return FHE_B200_OK;
-  if (k->par->device >= 0) cudaSetDevice(k->par->device);
-  cudaFree(k->k0);
-  cudaFree(k->k1);
-  cudaGetLastError();
+  {
+    ScopedDevice g(k->par->device);
+    cudaFree(k->k0);
+    cudaFree(k->k1);
+    cudaGetLastError();
+  }
   params_release(k->par);
   delete k;
   return FHE_B200_OK;
@@ -1103,7 +1136,7 @@ int fhe_b200_multiplicator_create(const fhe_b200_params* p, uint32_t level, cons
 int fhe_b200_multiplicator_free(fhe_b200_multiplicator* m) {
   if (!m) return FHE_B200_OK;
   if (m->par->device >= 0) {
-    cudaSetDevice(m->par->device);
+    ScopedDevice g(m->par->device);
     for (void* d : m->d_allocs) cudaFree(d);
     cudaGetLastError();
   }

@@ -113,6 +113,11 @@ int fhe_b200_batch_download(const fhe_b200_batch* b, uint32_t first, uint32_t n,
 int fhe_b200_batch_download_async(const fhe_b200_batch* b, uint32_t first, uint32_t n, uint64_t* host, void* stream);
 /* Ciphertext::clone: dst <- src (same parameters, shape, level; representation is copied) */
 int fhe_b200_batch_copy(fhe_b200_batch* dst, const fhe_b200_batch* src, void* stream);
+/* Page-locked host staging memory for asynchronous uploads / downloads (cudaHostAlloc, portable across devices).
+ * write_combined != 0 asks for write-combining pages: faster for the device to read over PCIe and invisible to the
+ * CPU caches, slow for the CPU to read -- meant for upload-only buffers the host fills once, front to back. */
+int fhe_b200_host_alloc(size_t bytes, int write_combined, void** out);
+int fhe_b200_host_free(void* p);
 /* raw device pointer of the batch storage (for zero-copy producers such as bench.py). */
 int fhe_b200_batch_device_ptr(const fhe_b200_batch* b, uint64_t** dptr, size_t* n_words);
 
