@@ -474,11 +474,12 @@ def main():
         alg_bytes = 16.0 * NTT_CFG["degree"] * rows          # 16*N bytes per limb-NTT
         achieved = alg_bytes / (ntt_ms * 1e-3) / 1e9
         peak, how = peaks()
-        roof = {"bound": "hbm", "kernel": "ntt_fast_kernel<8,1,*> (cols pass) + ntt_fast_kernel<6,0,*> (rows pass): one batched %d-row NTT, N=2^14" % rows,
+        roof = {"bound": "hbm", "kernel": "ntt_tma_cols_kernel<8,*> (cols pass) + ntt_tma_rows_kernel<*> (rows pass), TMA-fed persistent: one batched %d-row NTT, N=2^14" % rows,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
                 "traffic": ntt_traffic(), "ms_per_launch": ntt_ms, "multiplier_pipe": ntt_multiplier_pipe(),
                 "note": "algorithmic bytes = 16*N per limb-NTT (SURVEY 8d). The transform is bound by the integer "
-                        "multiplier pipe, not by HBM: see issue_roofline and DESIGN.md section 3",
+                        "multiplier pipe, not by HBM: at the bare-butterfly peak (issue_roofline.peak) 16*N bytes per "
+                        "7.5*N/16 butterflies cap this fraction at 0.31; see DESIGN.md section 3.2",
                 # second roofline for the same launches: 62-bit Harvey/Shoup butterflies per second against the
                 # measured peak of this pool's B200 (bench_micro/bf_bench.cu: 3.42 butterflies/clk/SM at 1.9 GHz)
                 "issue_roofline": {"unit": "T butterflies/s",
