@@ -478,8 +478,9 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
                 "traffic": ntt_traffic(), "ms_per_launch": ntt_ms, "multiplier_pipe": ntt_multiplier_pipe(),
                 "note": "algorithmic bytes = 16*N per limb-NTT (SURVEY 8d). The transform is bound by the integer "
-                        "multiplier pipe, not by HBM: at the bare-butterfly peak (issue_roofline.peak) 16*N bytes per "
-                        "7.5*N/16 butterflies cap this fraction at 0.31; see DESIGN.md section 3.2",
+                        "multiplier pipe, not by HBM: an N-point transform is N/2*log2(N) butterflies for 16*N bytes, so "
+                        "the bare-butterfly peak (issue_roofline.peak) caps this fraction at 0.34 for N=2^14 (0.31 "
+                        "for N=2^15); see DESIGN.md section 3.2",
                 # second roofline for the same launches: 62-bit Harvey/Shoup butterflies per second against the
                 # measured peak of this pool's B200 (bench_micro/bf_bench.cu: 3.42 butterflies/clk/SM at 1.9 GHz)
                 "issue_roofline": {"unit": "T butterflies/s",
