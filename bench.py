@@ -236,7 +236,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=int(os.environ.get("FHE_BENCH_BATCH", "1024")))
-    ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("FHE_BENCH_E2E_BATCH", "256")))
+    # end-to-end batch per step and GPU: a step drains its pipeline (the last chunk's multiply and download have nothing
+    # to overlap with), so the larger the batch the closer the rate gets to the link: 256 -> 3100, 512 -> 3320,
+    # 1024 -> 3440 products/s on one B200 (copy-only ceiling 3550).  512 keeps the pinned staging at 11 GB per rank.
+    ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("FHE_BENCH_E2E_BATCH", "512")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -366,23 +369,55 @@ def main():
         p = ctypes.c_void_p()
         check(L.fhe_b200_host_alloc(Be * wpc * 8, 1 if write_combined else 0, ctypes.byref(p)))
         return torch.frombuffer((ctypes.c_char * (Be * wpc * 8)).from_address(p.value), dtype=torch.int64)
-    ha, hb, ho = staging(wc), staging(wc), staging(False)
+    while True:
+        try:
+            ha, hb, ho = staging(wc), staging(wc), staging(False)
+            break
+        except Exception:              # the host refused to pin that much: halve the end-to-end batch (all ranks alike)
+            if Be <= 2 * ch:
+                raise
+            ha = hb = ho = None
+            Be //= 2
+            Be -= Be % ch
+    if world > 1:                      # every rank runs the same end-to-end batch
+        bt = torch.tensor([Be], device="cuda")
+        dist.all_reduce(bt, op=dist.ReduceOp.MIN)
+        if int(bt.item()) != Be:
+            Be = int(bt.item())
+            ha, hb, ho = ha[: Be * wpc], hb[: Be * wpc], ho[: Be * wpc]
     ha.copy_(torch.as_tensor(DevArray(A.device_ptr(), Be * wpc), device="cuda"))
     hb.copy_(torch.as_tensor(DevArray(Bt.device_ptr(), Be * wpc), device="cuda"))
     torch.cuda.synchronize()
     n_slots = int(os.environ.get("FHE_BENCH_E2E_SLOTS", "3"))   # upload k+1 while k computes and k-1 downloads
     streams = [torch.cuda.Stream() for _ in range(n_slots)]
-    slots = [(F.Ciphertext(par, ch, 2), F.Ciphertext(par, ch, 2), F.Ciphertext(par, ch, 2)) for _ in streams]
+    # chunk plan: 32-pair chunks, the last 32 pairs tapered (16 + 8 + 8) so that the part of a step nothing overlaps --
+    # the multiply and download of the final chunk -- is short.  Every (stream, chunk size) has its own device batches.
+    plan, off_ct = [], 0
+    tail = [ch // 2, ch // 4, ch // 4] if (ch % 4 == 0 and Be >= 2 * ch and os.environ.get("FHE_BENCH_E2E_TAPER", "1") == "1") else [ch]
+    while off_ct + ch <= Be - ch:
+        plan.append((off_ct, ch))
+        off_ct += ch
+    for n_t in (tail if Be - off_ct == ch else [Be - off_ct]):
+        plan.append((off_ct, n_t))
+        off_ct += n_t
+    assert off_ct == Be
+    slots = {}
+
+    def slot(k, n_ct):
+        key = (k % n_slots, n_ct)
+        if key not in slots:
+            slots[key] = (F.Ciphertext(par, n_ct, 2), F.Ciphertext(par, n_ct, 2), F.Ciphertext(par, n_ct, 2))
+        return slots[key]
 
     def e2e_step():
-        for k in range(Be // ch):
+        for k, (first, n_ct) in enumerate(plan):
             st = streams[k % n_slots].cuda_stream
-            sa, sb, so = slots[k % n_slots]
-            off = k * ch * wpc * 8
-            check(L.fhe_b200_batch_upload(sa._h, 0, ch, ha.data_ptr() + off, st))
-            check(L.fhe_b200_batch_upload(sb._h, 0, ch, hb.data_ptr() + off, st))
+            sa, sb, so = slot(k, n_ct)
+            off = first * wpc * 8
+            check(L.fhe_b200_batch_upload(sa._h, 0, n_ct, ha.data_ptr() + off, st))
+            check(L.fhe_b200_batch_upload(sb._h, 0, n_ct, hb.data_ptr() + off, st))
             check(L.fhe_b200_mul_relin(sa._h, sb._h, rk.ksk._h, 0, so._h, st))
-            check(L.fhe_b200_batch_download_async(so._h, 0, ch, ho.data_ptr() + off, st))
+            check(L.fhe_b200_batch_download_async(so._h, 0, n_ct, ho.data_ptr() + off, st))
         for s_ in streams:
             check(L.fhe_b200_sync(s_.cuda_stream))
 
@@ -502,6 +537,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * words * 8,
                     "d2h_bytes_per_step": words * 8, "batch": Be, "streams": n_slots,
                     "upload_staging": "write-combined pinned" if wc else "pinned",
+                    "chunks": [n_ct for _, n_ct in plan][-6:], "n_chunks": len(plan),
                     "timing": "median of %d steps (wall clock around upload+multiply+download, max over ranks)" % e2e_steps,
                     "step_ms": [round(x * 1e3, 2) for x in step_s],
                     "pinned_copy_gbs": {"h2d": round(pcie["h2d"], 1), "d2h": round(pcie["d2h"], 1)}, "host_numa": numa,
