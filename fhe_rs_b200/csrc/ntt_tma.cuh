@@ -637,7 +637,7 @@ struct ColsCfg {
 };
 
 // one radix-2^NS round (stages t .. t+NS-1 of the in-tile transform) over the whole tile, in place
-template <int LOGP, bool INV, int NS, bool REDUCE>
+template <int LOGP, bool INV, int NS, bool REDUCE, bool ROLL = false>
 __device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, int t, u64 p, u64 p2, const LimbDev& L) {
   using namespace tma;
   constexpr u32 NT = 1u << LOGP;
@@ -645,7 +645,7 @@ __device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, int t, u64 p, u
   constexpr u32 UNITS = (1u << (LOGP + 4 - NS)) / NT;   // radix groups per thread: 2 (NS=3), 4, 8
   const int logstride = LOGP - t - NS;
   const u32 stride_bytes = 128u << logstride;
-#pragma unroll
+#pragma unroll(ROLL ? 1 : 8)
   for (u32 q = 0; q < UNITS; q++) {
     const u32 gid = threadIdx.x + q * NT;
     const u32 bcol = gid & 15, rest = gid >> 4;
@@ -678,7 +678,7 @@ __device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, int t, u64 p, u
 
 // REDUCE (forward only): reduce the source words modulo the row's prime as they are read (digit broadcast with
 // mixed modulus sizes, zq/mod.rs:756)
-template <int LOGP, bool INV, int STAGES, int MINB, bool REDUCE>
+template <int LOGP, bool INV, int STAGES, int MINB, bool REDUCE, bool ROLL = false>
 __global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32, MINB)
     ntt_tma_cols_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                         const NttTmaArgs A) {
@@ -774,16 +774,16 @@ __global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32, MINB)
     if (!INV) {
 #pragma unroll
       for (int r = 0; r < NR; r++) {
-        if (r == 0) cols_round<LOGP, false, 3, REDUCE>(buf, tw_base, 0, p, p2, *Lp);
-        else if (r < NR - 1) cols_round<LOGP, false, 3, false>(buf, tw_base, 3 * r, p, p2, *Lp);
-        else cols_round<LOGP, false, REM, false>(buf, tw_base, 3 * r, p, p2, *Lp);
+        if (r == 0) cols_round<LOGP, false, 3, REDUCE, ROLL>(buf, tw_base, 0, p, p2, *Lp);
+        else if (r < NR - 1) cols_round<LOGP, false, 3, false, ROLL>(buf, tw_base, 3 * r, p, p2, *Lp);
+        else cols_round<LOGP, false, REM, false, ROLL>(buf, tw_base, 3 * r, p, p2, *Lp);
         if (r < NR - 1) consumer_sync<NT>();
       }
     } else {
 #pragma unroll
       for (int r = NR - 1; r >= 0; r--) {
-        if (r < NR - 1) cols_round<LOGP, true, 3, false>(buf, tw_base, 3 * r, p, p2, *Lp);
-        else cols_round<LOGP, true, REM, false>(buf, tw_base, 3 * r, p, p2, *Lp);
+        if (r < NR - 1) cols_round<LOGP, true, 3, false, ROLL>(buf, tw_base, 3 * r, p, p2, *Lp);
+        else cols_round<LOGP, true, REM, false, ROLL>(buf, tw_base, 3 * r, p, p2, *Lp);
         if (r > 0) consumer_sync<NT>();
       }
     }

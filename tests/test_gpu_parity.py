@@ -853,3 +853,32 @@ def test_packed_mul_basis_batch(oracle, F):
         off = sum((qq - 1).bit_length() * 8 for qq in mp.to.moduli[:i])
         nb = (q - 1).bit_length()
         assert oracle.transcode_from_bytes(bytes(blobs[1, 0, off:off + nb * 8]), nb)[:64] == [int(v) for v in y[1, 0, i]]
+
+
+def test_mixed_sizes_through_tma_kernels(oracle, F):
+    """N = 2^13 with moduli of very different sizes: the key-switch digits (below the largest modulus) exceed four
+    times the smallest one, so the digit transform must reduce its source words as it reads them (zq/mod.rs:756,
+    rq/mod.rs:563-586) -- the REDUCE variant of the TMA cols kernel -- and the scaler's output limbs are not all
+    Solinas primes (per-tile scaler kernel).  Multiply + relinearize and a rotation against the oracle."""
+    degree, t, sizes = 1 << 13, 65537, [62, 40, 30]
+    opar = oracle.BfvParameters(degree, t, moduli_sizes=sizes)
+    gpar = F.BfvParameters(degree, t, moduli=opar.moduli)
+    rng = np.random.default_rng(813)
+    ctx = opar.context_at_level(0)
+    L = len(sizes)
+    kc, gc = _rand_rows(rng, ctx.moduli, (2, L), degree), _rand_rows(rng, ctx.moduli, (2, L), degree)
+    ork = oracle.RelinearizationKey.from_ksk(oracle.KeySwitchingKey.from_arrays(opar, kc[0], kc[1]))
+    grk = F.RelinearizationKey.from_arrays(gpar, kc[0], kc[1])
+    count = 5
+    a, b = _rand_rows(rng, ctx.moduli, (count, 2), degree), _rand_rows(rng, ctx.moduli, (count, 2), degree)
+    A, B = F.Ciphertext.from_host(gpar, a), F.Ciphertext.from_host(gpar, b)
+    P = F.Multiplicator.default(grk).multiply(A, B).to_host()
+    om = oracle.Multiplicator.default(ork)
+    for i in (0, count - 1):
+        exp = om.multiply(oracle.Ciphertext.from_array(opar, a[i], 0), oracle.Ciphertext.from_array(opar, b[i], 0))
+        assert (P[i] == exp.to_array()).all()
+    ogk = oracle.GaloisKey.__new__(oracle.GaloisKey)
+    ogk.exponent, ogk.ksk = 3, oracle.KeySwitchingKey.from_arrays(opar, gc[0], gc[1])
+    R = F.GaloisKey.from_arrays(gpar, 3, gc[0], gc[1]).relinearize(A).to_host()
+    for i in (0, count - 1):
+        assert (R[i] == ogk.relinearize(oracle.Ciphertext.from_array(opar, a[i], 0)).to_array()).all()
