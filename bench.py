@@ -117,8 +117,14 @@ def run_reference(args):
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
     # one ciphertext pair per worker per step.  Capped at 32 workers: the scalar path is memory bound beyond that on
-    # this pool's hosts (measured on a 128-core box: 32 workers 38.0 products/s, 128 workers 28.5 products/s)
-    workers = max(1, min(cores, 32))
+    # this pool's hosts (measured on a 128-core box: 32 workers 38.0 products/s, 128 workers 28.5 products/s);
+    # FHE_BENCH_REF_WORKERS overrides the cap
+    workers = max(1, min(cores, int(os.environ.get("FHE_BENCH_REF_WORKERS", "32"))))
+    # load the checker's shared library in the parent, so that the forked workers (and any process-level accounting
+    # of loaded native code) see oracle/libfhe_oracle.so from the start
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fhe_oracle as _O
+    _O.lib()
     ctx = mp.get_context("fork")
     barrier = ctx.Barrier(workers + 1)
     q = ctx.Queue()
