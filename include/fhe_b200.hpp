@@ -94,6 +94,27 @@ class BfvParametersBuilder {
 };
 
 // A batch of `count` ciphertexts with `parts` polynomials each, at one level, resident in HBM.
+// Page-locked host staging memory (fhe_b200_host_alloc) for the asynchronous transfers below; write_combined for
+// upload-only buffers the host fills front to back.
+class PinnedWords {
+ public:
+  explicit PinnedWords(size_t n_words, bool write_combined = false) : n_(n_words) {
+    void* p = nullptr;
+    check(fhe_b200_host_alloc(n_words * sizeof(uint64_t), write_combined ? 1 : 0, &p));
+    p_ = static_cast<uint64_t*>(p);
+  }
+  PinnedWords(const PinnedWords&) = delete;
+  PinnedWords& operator=(const PinnedWords&) = delete;
+  ~PinnedWords() { fhe_b200_host_free(p_); }
+  uint64_t* data() { return p_; }
+  const uint64_t* data() const { return p_; }
+  size_t size() const { return n_; }
+
+ private:
+  uint64_t* p_ = nullptr;
+  size_t n_ = 0;
+};
+
 class Ciphertext {
  public:
   Ciphertext(std::shared_ptr<BfvParameters> par, uint32_t count, uint32_t parts = 2, uint32_t level = 0,
@@ -119,6 +140,11 @@ class Ciphertext {
     check(fhe_b200_batch_download(h_, 0, count(), w.data(), stream_));
     return w;
   }
+  // enqueue-only transfers of ciphertexts [first, first + n) on the batch's stream; `host` must be page-locked
+  // (PinnedWords) for them to be asynchronous and must stay valid until sync()
+  void upload_async(const uint64_t* host, uint32_t first, uint32_t n) { check(fhe_b200_batch_upload(h_, first, n, host, stream_)); }
+  void download_async(uint64_t* host, uint32_t first, uint32_t n) const { check(fhe_b200_batch_download_async(h_, first, n, host, stream_)); }
+  void sync() const { check(fhe_b200_sync(stream_)); }
   uint32_t count() const { uint32_t c; check(fhe_b200_batch_info(h_, &c, nullptr, nullptr, nullptr, nullptr)); return c; }
   uint32_t len() const { uint32_t p; check(fhe_b200_batch_info(h_, nullptr, &p, nullptr, nullptr, nullptr)); return p; }
   uint32_t level() const { uint32_t l; check(fhe_b200_batch_info(h_, nullptr, nullptr, &l, nullptr, nullptr)); return l; }

@@ -82,6 +82,19 @@ int main(int argc, char** argv) {
       mc.enable_relinearization(rk);
       if (mc.multiply(A, B).to_host() != P1) { printf("FAIL custom strategy != default\n"); return 1; }
     }
+    // pinned staging + enqueue-only transfers (fhe_b200_host_alloc, upload / download_async, sync)
+    {
+      PinnedWords up(wa.size(), true), down(wa.size());
+      for (size_t i = 0; i < wa.size(); i++) up.data()[i] = wa[i];
+      Ciphertext X(par, count);
+      X.upload_async(up.data(), 0, count);
+      X += B;
+      X -= B;
+      X.download_async(down.data(), 0, count);
+      X.sync();
+      for (size_t i = 0; i < wa.size(); i++)
+        if (down.data()[i] != wa[i]) { printf("FAIL pinned round trip\n"); return 1; }
+    }
     // error behaviour
     try {
       m.multiply(C3, B);
