@@ -183,9 +183,38 @@ void run_tma_rows_v(const u64* in, u64 in_rows, u64* out, u64 out_rows, NttTmaAr
   }
   g_launches++;
 }
+// two polynomials per CTA iteration (ntt_tma_rows_pair_kernel); needs an even number of polynomials
+template <bool INV, int STAGES, int MINB>
+void run_tma_rows_pair(const u64* in, u64 in_rows, u64* out, u64 out_rows, NttTmaArgs A, cudaStream_t st) {
+  using Cfg = RowsCfg<kRowsRlog, STAGES>;
+  constexpr size_t smem = (size_t)STAGES * 2 * Cfg::TILE_BYTES + Cfg::TW_PAIRS * 16 + 2 * STAGES * 8 + 1024;
+  const CUtensorMap mi = rows_map(in, in_rows, A.logn, 4 * Cfg::R), mo = rows_map(out, out_rows, A.logn, 4 * Cfg::R);
+  A.tiles_per_row = (1u << (A.logn - 6)) / Cfg::R;
+  A.n_polys /= 2;   // pairs
+  A.tiles_total = A.lpp * A.tiles_per_row * A.n_polys;
+  const u32 grid = std::min<u64>(A.tiles_total, (u64)sm_count() * MINB);
+  if (!INV && A.lazy_out) {
+    auto k = ntt_tma_rows_pair_kernel<INV, kRowsRlog, STAGES, MINB, !INV>;
+    ensure_dynamic_smem((const void*)k, smem);
+    k<<<grid, Cfg::NT + 32, smem, st>>>(mi, mo, A);
+  } else {
+    auto k = ntt_tma_rows_pair_kernel<INV, kRowsRlog, STAGES, MINB, false>;
+    ensure_dynamic_smem((const void*)k, smem);
+    k<<<grid, Cfg::NT + 32, smem, st>>>(mi, mo, A);
+  }
+  g_launches++;
+}
+
 template <bool INV>
 void run_tma_rows(const u64* in, u64 in_rows, u64* out, u64 out_rows, const NttTmaArgs& A, cudaStream_t st) {
-  static const int v = tma_variant("FHE_B200_TMA_ROWS", 44);
+  // default: two polynomials per CTA iteration (4392 vs 4364 products/s, rotations 11402 vs 11251/s for the one-tile
+  // kernel at 4 buffers x 4 CTAs per SM, profiles/microbench_r2.txt); FHE_B200_TMA_ROWS = 44 | 26 select the one-tile
+  // kernel with that ring depth x CTAs per SM
+  static const int v = tma_variant("FHE_B200_TMA_ROWS", 2);
+  if (v == 2 && A.n_polys % 2 == 0 && !(A.digit_adjacent && A.n_dig % 2)) {
+    run_tma_rows_pair<INV, 3, 3>(in, in_rows, out, out_rows, A, st);
+    return;
+  }
   // (ring depth x CTAs per SM measured flat within 2% from 2x6 to 4x4, profiles/microbench_r2.txt)
   if (v == 26) run_tma_rows_v<INV, 2, 6>(in, in_rows, out, out_rows, A, st);
   else run_tma_rows_v<INV, 4, 4>(in, in_rows, out, out_rows, A, st);

@@ -11,7 +11,9 @@
 //   * the tiles of a launch are ordered limb-major, polynomial-minor, so consecutive tiles of a CTA use the SAME
 //     twiddles: they are staged in shared memory once per (limb, tile position) and read from there with
 //     `base + immediate` 128-bit loads (the rows pass used to fetch 16 KiB of twiddles from L2 per 8 KiB of data);
-//   * butterflies update the tile in place (one CTA barrier per radix-8 round, none for the tile hand-over).
+//   * butterflies update the tile in place (one CTA barrier per radix-8 round, none for the tile hand-over); the rows
+//     pass handles two polynomials per iteration, so one twiddle fetch, one hand-over and one barrier serve 48
+//     butterflies per thread.
 //
 // Layouts.  cols tile: [N1 points][16 columns] u64, 128-byte box rows, no swizzle: every radix-8 access of a warp is
 // 256 contiguous bytes (or two 128-byte rows 1 KiB apart).  rows tile: [R rows][64 points] seen as 128-byte box rows
@@ -399,6 +401,215 @@ __global__ void __launch_bounds__(RowsCfg<RLOG, STAGES>::NT + 32, MINB)
       inv_stages<3>(v, tw, p, p2, false, A.limbs[0]);
 #pragma unroll
       for (int e = 0; e < 8; e++) sts64(buf + off0[e], v[e]);
+    }
+    fence_proxy_async();            // the tile is read next by the TMA store (async proxy)
+    mbar_arrive(bar_done + 8 * s);
+    fresh = w.next();
+  }
+}
+
+// The same pass on TWO polynomials per iteration (tiles (p, p+1) of the same limb and tile position): one twiddle fetch,
+// one tile hand-over and one CTA barrier serve 48 butterflies per thread instead of 24.  A.n_polys counts PAIRS.
+template <bool INV, int RLOG, int STAGES, int MINB, bool LAZY>
+__global__ void __launch_bounds__(RowsCfg<RLOG, STAGES>::NT + 32, MINB)
+    ntt_tma_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                        const NttTmaArgs A) {
+  using namespace tma;
+  using Cfg = RowsCfg<RLOG, STAGES>;
+  constexpr u32 R = Cfg::R, NT = Cfg::NT, TILE_BYTES = Cfg::TILE_BYTES, STAGE_BYTES = 2 * TILE_BYTES;
+  extern __shared__ unsigned char smem_raw[];
+  const u32 base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // the 128-byte swizzle works on absolute address bits
+  const u32 tw_base = base + STAGES * STAGE_BYTES;
+  const u32 bar_full = tw_base + Cfg::TW_PAIRS * 16;
+  const u32 bar_done = bar_full + STAGES * 8;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_done + 8 * s, NT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const u32 lo = (u32)(((u64)A.tiles_total * blockIdx.x) / gridDim.x);
+  const u32 hi = (u32)(((u64)A.tiles_total * (blockIdx.x + 1)) / gridDim.x);
+  const u32 n = hi - lo;
+  const u32 box_rows_per_row = (1u << A.logn) >> 4;   // 128-byte box rows per polynomial row
+
+  if (threadIdx.x >= NT) {
+    // ---------------- producer: one thread moves every tile of this CTA in and out
+    if (threadIdx.x != NT) return;
+    prefetch_map(&tm_in);
+    prefetch_map(&tm_out);
+    TileWalk wl, ws;   // load cursor, store cursor
+    wl.init(lo, A.n_polys);
+    ws.init(lo, A.n_polys);
+    auto coord = [&](const TileWalk& w, bool input, u32 h) -> u32 {
+      const u32 j = w.jt / A.tiles_per_row, tau = w.jt - j * A.tiles_per_row;
+      const u32 poly = 2 * w.p + h;
+      const u32 row = (input && A.in_bcast) ? poly : out_row_of(A, poly, j);
+      return row * box_rows_per_row + tau * (4 * R);
+    };
+    u32 loaded = 0;
+    auto load_next = [&]() {
+      const u32 s = loaded % STAGES;
+      mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+      load_2d(base + s * STAGE_BYTES, &tm_in, 0, coord(wl, true, 0), bar_full + 8 * s);
+      load_2d(base + s * STAGE_BYTES + TILE_BYTES, &tm_in, 0, coord(wl, true, 1), bar_full + 8 * s);
+      wl.next();
+      loaded++;
+    };
+    while (loaded < n && loaded < (u32)STAGES) load_next();  // every buffer starts full
+    for (u32 i = 0; i < n; i++) {
+      const u32 s = i % STAGES;
+      mbar_wait(bar_done + 8 * s, (i / STAGES) & 1);         // the consumers have finished tile i (in place)
+      store_2d(&tm_out, 0, coord(ws, false, 0), base + s * STAGE_BYTES);
+      store_2d(&tm_out, 0, coord(ws, false, 1), base + s * STAGE_BYTES + TILE_BYTES);
+      bulk_commit();
+      ws.next();
+      if (loaded < n) {
+        bulk_wait_read<0>();                                 // the store has left shared memory: its buffer takes
+        load_next();                                         // tile i+STAGES while tiles i+1 .. are being computed
+      }
+    }
+    bulk_wait_all();
+    return;
+  }
+
+  // ---------------- consumers
+  const u32 tid = threadIdx.x;
+  const u32 x = tid & 7, b = tid >> 3;   // both rounds: b = matrix row inside the tile, x = a_lo (round 0) / a_hi (round 1)
+  // byte offsets inside a (1024-byte aligned) tile buffer, TMA 128-byte swizzle: word i lives in 16-byte chunk
+  // ((i>>1)&7) ^ ((i>>4)&7) of 128-byte row i>>4
+  u32 off0[8];   // round 0: words 64b + x + 8e (64-bit accesses)
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const u32 i = 64 * b + x + 8 * e;
+    off0[e] = ((i >> 4) << 7) | ((((i >> 1) & 7) ^ ((i >> 4) & 7)) << 4) | ((i & 1) << 3);
+  }
+  u32 off1[4];   // round 1: pairs (64b + 8x + 2k, +1) (128-bit accesses)
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const u32 i = 64 * b + 8 * x + 2 * k;
+    off1[k] = ((i >> 4) << 7) | ((((i >> 1) & 7) ^ ((i >> 4) & 7)) << 4);
+  }
+  // twiddle pair addresses: region tl starts at pair R*(2^tl - 1); stages 0..2 index (b << tl) + m, stages 3..5 are
+  // stored as 2^u planes of 8R pairs so that lane `tid` reads pair `tid` of plane m (unit stride across the warp)
+  const u32 tw0 = tw_base + 16 * (b);                       // tl = 0: region offset 0
+  const u32 tw1 = tw_base + 16 * (R * 1 + (b << 1));        // tl = 1
+  const u32 tw2 = tw_base + 16 * (R * 3 + (b << 2));        // tl = 2
+  const u32 tw3 = tw_base + 16 * (R * 7 + tid);             // tl = 3: 1 plane
+  const u32 tw4 = tw_base + 16 * (R * 15 + tid);            // tl = 4: 2 planes of 8R
+  const u32 tw5 = tw_base + 16 * (R * 31 + tid);            // tl = 5: 4 planes of 8R
+
+  TileWalk w;
+  w.init(lo, A.n_polys);
+  bool fresh = true;
+  u64 p = 0, p2 = 0;
+  const u32 logn1 = A.logn - 6;
+  for (u32 i = 0; i < n; i++) {
+    if (fresh) {
+      // new (limb, tile position): stage its 63R twiddle pairs (omegas[(1<<s) + (row0<<tl) + k] forward,
+      // zetas_inv[N - (2<<s) + (row0<<tl) + k] inverse, s = logn1 + tl; ntt/native.rs:44-56)
+      const u32 j = w.jt / A.tiles_per_row, tau = w.jt - j * A.tiles_per_row;
+      const LimbDev& L = A.limbs[A.ids[j]];
+      p = L.p;
+      p2 = L.p2;
+      const ulonglong2* tab = INV ? L.zi : L.om;
+      const u32 row0 = tau * R;
+      if (i) consumer_sync<NT>();   // nobody still reads the previous twiddles
+#pragma unroll
+      for (int tl = 0; tl < 6; tl++) {
+        const u32 s = logn1 + tl;
+        const u32 g0 = (INV ? ((1u << A.logn) - (2u << s)) : (1u << s)) + (row0 << tl);
+        for (u32 k = tid; k < (R << tl); k += NT) {
+          const ulonglong2 v = __ldg(tab + g0 + k);
+          const u32 dst = tl < 3 ? k : (k & ((1u << (tl >= 3 ? tl - 3 : 0)) - 1)) * (8 * R) + (k >> (tl >= 3 ? tl - 3 : 0));
+          sts128(tw_base + 16 * (R * ((1u << tl) - 1) + dst), v.x, v.y);
+        }
+      }
+      consumer_sync<NT>();
+    }
+    const u32 s = i % STAGES;
+    const u32 buf0 = base + s * STAGE_BYTES;
+    mbar_wait(bar_full + 8 * s, (i / STAGES) & 1);
+    u64 v[8];
+    ulonglong2 tw[7];
+    // first round of the pass on both tiles (twiddles fetched once), barrier, second round on both tiles
+    if (!INV) {
+      tw[0] = lds128(tw0);
+      tw[1] = lds128(tw1);
+      tw[2] = lds128(tw1 + 16);
+#pragma unroll
+      for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw2 + 16 * m);
+    } else {
+      tw[0] = lds128(tw3);
+      tw[1] = lds128(tw4);
+      tw[2] = lds128(tw4 + 16 * 8 * R);
+#pragma unroll
+      for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw5 + 16 * 8 * R * m);
+    }
+#pragma unroll
+    for (u32 h = 0; h < 2; h++) {
+      const u32 buf = buf0 + h * TILE_BYTES;
+      if (!INV) {   // round 0: strides 32, 16, 8
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = lds64(buf + off0[e]);
+        fwd_stages<3>(v, tw, p, p2);
+#pragma unroll
+        for (int e = 0; e < 8; e++) sts64(buf + off0[e], v[e]);
+      } else {      // inverse starts with round 1: strides 1, 2, 4
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const ulonglong2 t = lds128(buf + off1[k]);
+          v[2 * k] = t.x;
+          v[2 * k + 1] = t.y;
+        }
+        inv_stages<3>(v, tw, p, p2, false, A.limbs[0]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) sts128(buf + off1[k], v[2 * k], v[2 * k + 1]);
+      }
+    }
+    consumer_sync<NT>();
+    if (!INV) {
+      tw[0] = lds128(tw3);
+      tw[1] = lds128(tw4);
+      tw[2] = lds128(tw4 + 16 * 8 * R);
+#pragma unroll
+      for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw5 + 16 * 8 * R * m);
+    } else {
+      tw[0] = lds128(tw0);
+      tw[1] = lds128(tw1);
+      tw[2] = lds128(tw1 + 16);
+#pragma unroll
+      for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw2 + 16 * m);
+    }
+#pragma unroll
+    for (u32 h = 0; h < 2; h++) {
+      const u32 buf = buf0 + h * TILE_BYTES;
+      if (!INV) {   // round 1: strides 4, 2, 1, then reduce3 unless lazy (native.rs:178-180, :238)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const ulonglong2 t = lds128(buf + off1[k]);
+          v[2 * k] = t.x;
+          v[2 * k + 1] = t.y;
+        }
+        fwd_stages<3>(v, tw, p, p2);
+        if (!LAZY) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) v[e] = fwd_final<false>(v[e], p, p2, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) sts128(buf + off1[k], v[2 * k], v[2 * k + 1]);
+      } else {      // round 0: strides 8, 16, 32
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = lds64(buf + off0[e]);
+        inv_stages<3>(v, tw, p, p2, false, A.limbs[0]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) sts64(buf + off0[e], v[e]);
+      }
     }
     fence_proxy_async();            // the tile is read next by the TMA store (async proxy)
     mbar_arrive(bar_done + 8 * s);

@@ -430,7 +430,7 @@ def test_wide_golden_fixture(F):
 @pytest.mark.parametrize("env", [{"FHE_B200_SOLINAS_NTT": "1"}, {"FHE_B200_NO_SOLINAS": "1"}, {"FHE_B200_GENERIC_NTT": "1"},
                                  {"FHE_B200_CHUNK": "1"}, {"FHE_B200_ROWS_TLOG": "12", "FHE_B200_COLS_TLOG": "12"},
                                  {"FHE_B200_NTT": "tma"}, {"FHE_B200_NTT": "fast"},
-                                 {"FHE_B200_NTT": "tma", "FHE_B200_CHUNK": "1"}, {"FHE_B200_SCALER": "classic"}, {"FHE_B200_KSMAC": "classic"}, {"FHE_B200_NO_TENSOR_FUSION": "1"}])
+                                 {"FHE_B200_NTT": "tma", "FHE_B200_CHUNK": "1"}, {"FHE_B200_SCALER": "classic"}, {"FHE_B200_KSMAC": "classic"}, {"FHE_B200_NO_TENSOR_FUSION": "1"}, {"FHE_B200_NTT": "tma", "FHE_B200_TMA_ROWS": "44"}])
 def test_alternate_code_paths(F, env):
     """the optional arithmetic / kernel variants (Solinas twiddle pairs, Barrett-only folds, generic tile NTT,
     one-ciphertext chunks, 4096-word NTT tiles) must be bit-identical too: rerun the set-A multiply + the 2^13 NTT test under each switch"""
