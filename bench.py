@@ -515,7 +515,7 @@ def main():
         alg_bytes = 16.0 * NTT_CFG["degree"] * rows          # 16*N bytes per limb-NTT
         achieved = alg_bytes / (ntt_ms * 1e-3) / 1e9
         peak, how = peaks()
-        roof = {"bound": "hbm", "kernel": "ntt_tma_cols_kernel<8,*> (cols pass) + ntt_tma_rows_kernel<*> (rows pass), TMA-fed persistent: one batched %d-row NTT, N=2^14" % rows,
+        roof = {"bound": "hbm", "kernel": "ntt_tma_cols_kernel<8,*> (cols pass) + ntt_tma_rows_pair_kernel<*> (rows pass), TMA-fed persistent: one batched %d-row NTT, N=2^14" % rows,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
                 "traffic": ntt_traffic(), "ms_per_launch": ntt_ms, "multiplier_pipe": ntt_multiplier_pipe(),
                 "note": "algorithmic bytes = 16*N per limb-NTT (SURVEY 8d). The transform is bound by the integer "
