@@ -773,16 +773,19 @@ __global__ void __launch_bounds__(TensorRowsCfg<RLOG, STAGES>::NT + 32, MINB)
     const u32 s = i % STAGES;
     const u32 buf = base + s * STAGE_BYTES;
     mbar_wait(bar_full + 8 * s, (i / STAGES) & 1);
-    // point-wise products of this thread's 8 consecutive positions of the tile
-    u64 v0[8], v1[8], v2[8];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const ulonglong2 a0 = lds128(buf + off1[k]), a1 = lds128(buf + TILE_BYTES + off1[k]);
-      const ulonglong2 b0 = lds128(buf + 2 * TILE_BYTES + off1[k]), b1 = lds128(buf + 3 * TILE_BYTES + off1[k]);
-      v0[2 * k] = mulmod_limb(a0.x, b0.x, M);
-      v0[2 * k + 1] = mulmod_limb(a0.y, b0.y, M);
-      v2[2 * k] = mulmod_limb(a1.x, b1.x, M);
-      v2[2 * k + 1] = mulmod_limb(a1.y, b1.y, M);
+    // Phase 1: point-wise products of this thread's 8 consecutive positions, two per trip, deposited over the
+    // consumed operands (c0 -> a0 buffer, c1 -> b0 buffer, c2 -> a1 buffer; only this thread touches those words).
+    // The loops over trips and tiles are rolled on purpose: fully unrolled the kernel was ~64 KB of code and lost
+    // 0.68 issue slots per issued instruction to instruction fetch (profiles/r2_tensor_rows_kernel.txt).
+#pragma unroll 1
+    for (u32 k = 0; k < 4; k++) {
+      const u32 i = 64 * b + 8 * x + 2 * k;
+      const u32 o = buf + (((i >> 4) << 7) | ((((i >> 1) & 7) ^ ((i >> 4) & 7)) << 4));
+      const ulonglong2 a0 = lds128(o), a1 = lds128(o + TILE_BYTES);
+      const ulonglong2 b0 = lds128(o + 2 * TILE_BYTES), b1 = lds128(o + 3 * TILE_BYTES);
+      // (residues in [0,2p): the inverse butterflies that consume them take lazy operands, native.rs:303-316)
+      const u64 c0x = mulmod_limb_lazy(a0.x, b0.x, M), c0y = mulmod_limb_lazy(a0.y, b0.y, M);
+      const u64 c2x = mulmod_limb_lazy(a1.x, b1.x, M), c2y = mulmod_limb_lazy(a1.y, b1.y, M);
       Acc192 sx, sy;                               // a0*b1 + a1*b0 < 2^125, one reduction
       sx.clear();
       sy.clear();
@@ -790,40 +793,47 @@ __global__ void __launch_bounds__(TensorRowsCfg<RLOG, STAGES>::NT + 32, MINB)
       sx.mac(a1.x, b0.x);
       sy.mac(a0.y, b1.y);
       sy.mac(a1.y, b0.y);
-      v1[2 * k] = sx.reduce(M);
-      v1[2 * k + 1] = sy.reduce(M);
+      const u64 c1x = sx.reduce_lazy(M), c1y = sy.reduce_lazy(M);
+      sts128(o, c0x, c0y);
+      sts128(o + 2 * TILE_BYTES, c1x, c1y);
+      sts128(o + TILE_BYTES, c2x, c2y);
     }
-    // inverse round 1 (strides 1, 2, 4) of the three product tiles, deposited over the consumed operand tiles
+    // Phase 2: inverse round 1 (strides 1, 2, 4) of the three product tiles: the same 8 positions, same thread
+    u64 v[8];
     ulonglong2 tw[7];
     tw[0] = lds128(tw3);
     tw[1] = lds128(tw4);
     tw[2] = lds128(tw4 + 16 * 8 * R);
 #pragma unroll
     for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw5 + 16 * 8 * R * m);
-    inv_stages<3>(v0, tw, p, p2, false, M);
-    inv_stages<3>(v1, tw, p, p2, false, M);
-    inv_stages<3>(v2, tw, p, p2, false, M);
+#pragma unroll 1
+    for (u32 t = 0; t < 3; t++) {
+      const u32 tb = buf + t * TILE_BYTES;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      sts128(buf + off1[k], v0[2 * k], v0[2 * k + 1]);                     // c0 -> a0 buffer
-      sts128(buf + 2 * TILE_BYTES + off1[k], v1[2 * k], v1[2 * k + 1]);    // c1 -> b0 buffer
-      sts128(buf + TILE_BYTES + off1[k], v2[2 * k], v2[2 * k + 1]);        // c2 -> a1 buffer
+      for (int k = 0; k < 4; k++) {
+        const ulonglong2 q = lds128(tb + off1[k]);
+        v[2 * k] = q.x;
+        v[2 * k + 1] = q.y;
+      }
+      inv_stages<3>(v, tw, p, p2, false, M);
+#pragma unroll
+      for (int k = 0; k < 4; k++) sts128(tb + off1[k], v[2 * k], v[2 * k + 1]);
     }
     consumer_sync<NT>();
-    // inverse round 0 (strides 8, 16, 32) of each product tile
+    // Phase 3: inverse round 0 (strides 8, 16, 32) of each product tile
     tw[0] = lds128(tw0);
     tw[1] = lds128(tw1);
     tw[2] = lds128(tw1 + 16);
 #pragma unroll
     for (int m = 0; m < 4; m++) tw[3 + m] = lds128(tw2 + 16 * m);
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
+#pragma unroll 1
+    for (u32 t = 0; t < 3; t++) {
       const u32 tb = buf + t * TILE_BYTES;
 #pragma unroll
-      for (int e = 0; e < 8; e++) v0[e] = lds64(tb + off0[e]);
-      inv_stages<3>(v0, tw, p, p2, false, M);
+      for (int e = 0; e < 8; e++) v[e] = lds64(tb + off0[e]);
+      inv_stages<3>(v, tw, p, p2, false, M);
 #pragma unroll
-      for (int e = 0; e < 8; e++) sts64(tb + off0[e], v0[e]);
+      for (int e = 0; e < 8; e++) sts64(tb + off0[e], v[e]);
     }
     fence_proxy_async();
     mbar_arrive(bar_done + 8 * s);

@@ -339,6 +339,18 @@ struct Acc192 {
     lo = ((u64)w1 << 32) | e0;
     mid = ((u64)w3 << 32) | w2;
   }
+  // residue in [0,2p) of the accumulated value (which must be < 2^160)
+  __device__ __forceinline__ u64 reduce_lazy(const LimbDev& m) const {
+    u64 lo, mid;
+    u32 hi32;
+    merged(lo, mid, hi32);
+    const u64 hi = hi32;
+    if (m.sol_c) return fold192_solinas(lo, mid, hi, (u32)m.sol_c);
+    u64 r1 = barrett128_lazy(lo, mid, m.p, m.bhi, m.blo);  // [0,2p)
+    u64 hl = hi * m.c128, hh = __umul64hi(hi, m.c128);
+    u64 r2 = barrett128_lazy(hl, hh, m.p, m.bhi, m.blo);   // [0,2p)
+    return csub(r1 + r2, m.p2);
+  }
   // canonical residue of the accumulated value (which must be < 2^160)
   __device__ __forceinline__ u64 reduce(const LimbDev& m) const {
     u64 lo, mid;
@@ -475,6 +487,16 @@ struct AccTheta {
     w[6] = (u32)t;
   }
 };
+
+// a*b mod p in [0,2p) for canonical a, b: for consumers that accept lazy operands (the inverse butterflies)
+__device__ __forceinline__ u64 mulmod_limb_lazy(u64 a, u64 b, const LimbDev& m) {
+  if (m.sol_c) {
+    u64 lo, hi;
+    mul128_62(a, b, lo, hi);
+    return fold192_solinas(lo, hi, 0, (u32)m.sol_c);
+  }
+  return barrett128_lazy(a * b, __umul64hi(a, b), m.p, m.bhi, m.blo);
+}
 
 // canonical a*b mod p for canonical a, b (Modulus::mul / mul_opt, zq/mod.rs:131-156)
 __device__ __forceinline__ u64 mulmod_limb(u64 a, u64 b, const LimbDev& m) {
