@@ -147,10 +147,15 @@ __device__ __forceinline__ void fwd_stages(u64* v, const ulonglong2* tw, u64 p, 
     }
   }
 }
+// constants of the last inverse stage (N^-1 and zetas_inv[N-2] * N^-1 with their Shoup companions), held in
+// registers by the kernels that reach it
+struct LastStage {
+  u64 ninv, ninv_s, zn, zn_s;
+};
 // NS Gentleman-Sande stages, innermost stage first (ntt/native.rs:120-136); `last`: stage u == 0 is the transform's
 // final stage, fused with the N^-1 scaling (native.rs:230-232)
-template <int NS>
-__device__ __forceinline__ void inv_stages(u64* v, const ulonglong2* tz, u64 p, u64 p2, bool last, const LimbDev& L) {
+template <int NS, typename LS>
+__device__ __forceinline__ void inv_stages(u64* v, const ulonglong2* tz, u64 p, u64 p2, bool last, const LS& L) {
   constexpr int R = 1 << NS;
 #pragma unroll
   for (int u = NS - 1; u >= 0; u--) {
@@ -861,7 +866,7 @@ struct ColsCfg {
 // The radix groups of a thread differ by compile-time address / twiddle offsets.  ROLL keeps the loop over them rolled
 // (half the code); measured slower than the unrolled form (4434 vs 4451 products/s), which stays the default.
 template <int LOGP, bool INV, int NS, int T, bool REDUCE, bool ROLL = false>
-__device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, u64 p, u64 p2, const LimbDev& L) {
+__device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, u64 p, u64 p2, const tma::LastStage& L, u64 bhi, u64 blo) {
   using namespace tma;
   constexpr int t = T;
   constexpr u32 NT = 1u << LOGP;
@@ -883,7 +888,7 @@ __device__ __forceinline__ void cols_round(u32 buf, u32 tw_base, u64 p, u64 p2, 
 #pragma unroll
     for (int e = 0; e < R; e++) {
       v[e] = lds64(addr + e * stride_bytes);
-      if (REDUCE) v[e] = barrett64(v[e], L.p, L.bhi, L.blo);
+      if (REDUCE) v[e] = barrett64(v[e], p, bhi, blo);
     }
     ulonglong2 tw[R - 1];
 #pragma unroll
@@ -978,7 +983,8 @@ __global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32, MINB)
   w.init(lo, A.n_polys);
   u32 cur_j = 0xffffffffu;
   const LimbDev* Lp = A.limbs;
-  u64 p = 0, p2 = 0;
+  u64 p = 0, p2 = 0, bhi = 0, blo = 0;
+  LastStage ls = {0, 0, 0, 0};
   for (u32 i = 0; i < n; i++) {
     const u32 j = w.jt / A.tiles_per_row;
     if (j != cur_j) {
@@ -986,6 +992,11 @@ __global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32, MINB)
       Lp = A.limbs + A.ids[j];
       p = Lp->p;
       p2 = Lp->p2;
+      if (INV) ls = LastStage{Lp->ninv, Lp->ninv_s, Lp->zn, Lp->zn_s};   // loop-invariant per limb: out of the hot loop
+      if (REDUCE) {
+        bhi = Lp->bhi;
+        blo = Lp->blo;
+      }
       const ulonglong2* tab = INV ? Lp->zi + ((1u << A.logn) - P) : Lp->om;
       if (cur_j != 0xffffffffu) consumer_sync<NT>();
       for (u32 k = tid; k < P; k += NT) {
@@ -1001,17 +1012,17 @@ __global__ void __launch_bounds__(ColsCfg<LOGP, STAGES>::NT + 32, MINB)
     if (!INV) {
 #pragma unroll
       for (int r = 0; r < NR; r++) {
-        if (r == 0) cols_round<LOGP, false, 3, 0, REDUCE, ROLL>(buf, tw_base, p, p2, *Lp);
-        else if (r == 1 && NR > 2) cols_round<LOGP, false, 3, 3, false, ROLL>(buf, tw_base, p, p2, *Lp);
-        else cols_round<LOGP, false, REM, 3 * (NR - 1), false, ROLL>(buf, tw_base, p, p2, *Lp);
+        if (r == 0) cols_round<LOGP, false, 3, 0, REDUCE, ROLL>(buf, tw_base, p, p2, ls, bhi, blo);
+        else if (r == 1 && NR > 2) cols_round<LOGP, false, 3, 3, false, ROLL>(buf, tw_base, p, p2, ls, bhi, blo);
+        else cols_round<LOGP, false, REM, 3 * (NR - 1), false, ROLL>(buf, tw_base, p, p2, ls, bhi, blo);
         if (r < NR - 1) consumer_sync<NT>();
       }
     } else {
 #pragma unroll
       for (int r = NR - 1; r >= 0; r--) {
-        if (r == 0) cols_round<LOGP, true, 3, 0, false, ROLL>(buf, tw_base, p, p2, *Lp);
-        else if (r == 1 && NR > 2) cols_round<LOGP, true, 3, 3, false, ROLL>(buf, tw_base, p, p2, *Lp);
-        else cols_round<LOGP, true, REM, 3 * (NR - 1), false, ROLL>(buf, tw_base, p, p2, *Lp);
+        if (r == 0) cols_round<LOGP, true, 3, 0, false, ROLL>(buf, tw_base, p, p2, ls, bhi, blo);
+        else if (r == 1 && NR > 2) cols_round<LOGP, true, 3, 3, false, ROLL>(buf, tw_base, p, p2, ls, bhi, blo);
+        else cols_round<LOGP, true, REM, 3 * (NR - 1), false, ROLL>(buf, tw_base, p, p2, ls, bhi, blo);
         if (r > 0) consumer_sync<NT>();
       }
     }
