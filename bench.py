@@ -333,7 +333,7 @@ def main():
 
     # ---- parity of the timed work, outside the timed region: products / rotations whose indices span the internal
     # chunks are compared with the CPU oracle on every rank; no `value` is printed unless all of them are bit-exact
-    idx = sorted(set(i for i in ((0, 127, 128, B - 1) if rank == 0 else (0, B - 1)) if 0 <= i < B))
+    idx = sorted(set(i for i in ((0, 255, 256, B - 1) if rank == 0 else (0, B - 1)) if 0 <= i < B))   # 256 = the library's chunk
     ok_mul, ok_rot = verify_against_oracle(np, A, Bt, out, rot, kc, gc, idx)
     okt = torch.tensor([int(ok_mul), int(ok_rot)], device="cuda")
     if world > 1:

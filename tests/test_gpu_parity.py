@@ -714,7 +714,7 @@ def _rand_rows(rng, moduli, shape_prefix, degree):
 @pytest.mark.parametrize("variant", ["plain", "mod_switch", "key_level_0_ct_level_1"])
 def test_set_c_across_chunk_boundary(oracle, F, variant):
     """The shape the headline number is measured on (N = 2^15, 14 x 62-bit) with MORE ciphertexts than one internal
-    chunk (128): products 0, 127, 128, 129 of a 130-pair batch and rotations 0 / 128 / 129 are compared with the
+    chunk (256): products 0, 255, 256, 257 of a 258-pair batch and rotations 0 / 256 / 257 are compared with the
     oracle, so the chunk loop, its tail chunk and every per-chunk offset of mul_relin / galois are covered --
     plain, with modulus switching (mul.rs:296-330), and with a level-0 key serving level-1 ciphertexts
     (relinearization_key.rs:88-95, galois_key.rs:69-76)."""
@@ -734,7 +734,7 @@ def test_set_c_across_chunk_boundary(oracle, F, variant):
     ogk = oracle.GaloisKey.__new__(oracle.GaloisKey)
     ogk.exponent, ogk.ksk = 3, oracle.KeySwitchingKey.from_arrays(opar, gc[0], gc[1], ct_level, 0)
     ggk = F.GaloisKey.from_arrays(gpar, 3, gc[0], gc[1], ciphertext_level=ct_level, key_level=0)
-    count = 130
+    count = 258
     a = _rand_rows(rng, ct_mod, (count, 2), degree)
     b = _rand_rows(rng, ct_mod, (count, 2), degree)
     A = F.Ciphertext.from_host(gpar, a, level=ct_level)
@@ -746,12 +746,12 @@ def test_set_c_across_chunk_boundary(oracle, F, variant):
     out = gm.multiply(A, B)
     assert out.level == ct_level + (1 if variant == "mod_switch" else 0)
     P = out.to_host()
-    for i in (0, 127, 128, 129):
+    for i in (0, 255, 256, 257):
         exp = om.multiply(oracle.Ciphertext.from_array(opar, a[i], ct_level),
                           oracle.Ciphertext.from_array(opar, b[i], ct_level))
         assert (P[i] == exp.to_array()).all(), "product %d differs" % i
     R = ggk.relinearize(A).to_host()
-    for i in (0, 128, 129):
+    for i in (0, 256, 257):
         exp = ogk.relinearize(oracle.Ciphertext.from_array(opar, a[i], ct_level))
         assert (R[i] == exp.to_array()).all(), "rotation %d differs" % i
     if variant == "plain":
