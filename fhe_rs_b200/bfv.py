@@ -16,11 +16,12 @@ from typing import Dict, Optional, Sequence
 
 import numpy as np
 
-from . import _capi
+from . import _capi, wire
 from ._capi import NTT, POWER_BASIS, FheError, check
+from .wire import WireError
 
 __all__ = ["BfvParameters", "BfvParametersBuilder", "Ciphertext", "KeySwitchingKey", "RelinearizationKey", "RGSWCiphertext",
-           "GaloisKey", "EvaluationKey", "Multiplicator", "ScalingFactor", "dot_product_scalar", "FheError", "NTT", "POWER_BASIS"]
+           "GaloisKey", "EvaluationKey", "Multiplicator", "ScalingFactor", "dot_product_scalar", "FheError", "WireError", "NTT", "POWER_BASIS"]
 
 
 def _release(free_name: str, handle) -> None:
@@ -282,6 +283,53 @@ class Ciphertext:
         check(_capi.lib().fhe_b200_sync(stream))
         return ct
 
+    # -- protobuf messages (bfv/ciphertext.rs:230-317; fhe_traits::Serialize / DeserializeParametrized)
+    def to_bytes(self) -> list:
+        """`ct.to_bytes()` for every ciphertext of the batch: one encoded fhers.bfv.Ciphertext each, every part an
+        fhers.rq.Rq with representation NTT (the unseeded branch of ciphertext.rs:240-252).  The coefficient packing
+        runs on the device; only the few bytes of framing are host work."""
+        c, p, lv, _, r = self._info()
+        if r != NTT:
+            raise FheError(_capi.INVALID_REPRESENTATION, "Ciphertext polynomials are Poly<Ntt> (ciphertext.rs:18-32)")
+        blobs = self.to_packed()
+        self.sync()
+        deg = self.par.degree()
+        return [wire.encode_ciphertext([wire.encode_rq(wire.REP_NTT, deg, memoryview(blobs[i, j])) for j in range(p)],
+                                       b"", lv) for i in range(c)]
+
+    @staticmethod
+    def from_bytes(par: "BfvParameters", messages: Sequence[bytes], seeded_halves: Optional[np.ndarray] = None,
+                   stream: int = 0) -> "Ciphertext":
+        """`Ciphertext::from_bytes(bytes, &par)` (ciphertext.rs:259-317) for a batch of messages of one level and part
+        count.  A message that carries a seed instead of its last polynomial needs `seeded_halves[i]`: the NTT words
+        [limbs][N] of `Poly::random_from_seed(ctx, seed)`, expanded by the Rust host (include/fhe_b200.h explains why
+        the device does not)."""
+        if len(messages) == 0:
+            raise FheError(_capi.INVALID_ARGUMENT, "no messages")
+        dec = [wire.decode_ciphertext(m) for m in messages]
+        level = dec[0][2]
+        if level > par.max_level():
+            raise WireError("InvalidLevel", _capi.INVALID_LEVEL, "level %d, max %d" % (level, par.max_level()))
+        n_rq = len(dec[0][0])
+        seeded = bool(dec[0][1])
+        for c, seed, lv in dec:
+            if lv != level or len(c) != n_rq or bool(seed) != seeded:
+                raise FheError(_capi.INVALID_ARGUMENT, "a batch holds ciphertexts of one level, part count and kind")
+            if seed and len(seed) != 32:
+                raise WireError("InvalidSeedSize", detail="%d bytes, expected 32" % len(seed))
+        body = Ciphertext(par, len(dec), n_rq, level, NTT, stream)
+        _unpack_rq(body, [c for c, _, _ in dec], wire.REP_NTT)
+        if not seeded:
+            return body
+        if seeded_halves is None:
+            raise WireError("SeedExpansion", _capi.UNSUPPORTED,
+                            "the message carries a seed: pass the host-expanded last polynomial (ciphertext.rs:287-300)")
+        halves = np.ascontiguousarray(seeded_halves, dtype=np.uint64)
+        if halves.shape != (len(dec), body.limbs, par.degree()):
+            raise FheError(_capi.INVALID_ARGUMENT, "expected seeded_halves as [count][limbs][N]")
+        words = np.concatenate([body.to_host(), halves[:, None]], axis=1)
+        return Ciphertext.from_host(par, words, level, NTT, stream)
+
     def device_ptr(self) -> int:
         p, n = C.c_void_p(), C.c_size_t()
         check(_capi.lib().fhe_b200_batch_device_ptr(self._h, C.byref(p), C.byref(n)))
@@ -375,7 +423,7 @@ class Ciphertext:
         return self
 
     def substitute(self, exponent: int) -> "Ciphertext":
-        """Poly::substitute on every polynomial (rq/mod.rs:360-389)."""
+        """Poly::substitute on every polynomial, in either representation (rq/mod.rs:360-408)."""
         out = self._like()
         check(_capi.lib().fhe_b200_substitute(self._h, exponent, out._h, self.stream))
         return out
@@ -386,6 +434,31 @@ class Ciphertext:
         out = Ciphertext(self.par, c, p, lv, r, self.stream, mul_basis=(which == 0))
         check(_capi.lib().fhe_b200_scale(self._h, which, out._h, self.stream))
         return out
+
+
+def _unpack_rq(batch: "Ciphertext", rq_messages, want_rep: int) -> None:
+    """`Poly::<R>::from_bytes(bytes, ctx)` (rq/serialize.rs:23-31 -> rq/convert.rs:46-161) for every polynomial of
+    `batch`: rq_messages[i][j] is the encoded Rq of part j of ciphertext i.  Framing and checks here, unpacking (and
+    the forward NTT of an NTT batch) on the device."""
+    par, nbytes = batch.par, batch.packed_bytes_per_poly()
+    count, parts = batch.count, len(batch)
+    limbs, deg = batch.limbs, par.degree()
+    blobs = np.zeros((count, parts, nbytes), np.uint8)
+    for i, polys in enumerate(rq_messages):
+        for j, msg in enumerate(polys):
+            rep, degree, coeffs = wire.decode_rq(msg)
+            if degree * nbytes != len(coeffs) * deg:          # sum_i serialization_length(degree) (convert.rs:76-88)
+                raise WireError("InvalidCoefficientCount", detail="%d bytes for degree %d" % (len(coeffs), degree))
+            if rep != want_rep:
+                raise WireError("RepresentationMismatch", _capi.INVALID_REPRESENTATION,
+                                "found %d, expected %d" % (rep, want_rep))
+            if degree != deg and (limbs != 1 or degree > deg):
+                # TryConvertFrom<Vec<u64>> for Poly<PowerBasis> (convert.rs:148-192): q.len() * degree words, or -- one
+                # modulus only -- a shorter low-order polynomial, zero-extended (the zero bytes already in `blobs`)
+                raise WireError("InvalidCoefficientCount", detail="degree %d in a context of degree %d" % (degree, deg))
+            blobs[i, j, :len(coeffs)] = np.frombuffer(coeffs, np.uint8)
+    check(_capi.lib().fhe_b200_batch_unpack(batch._h, 0, count, _ptr(blobs), batch.stream))
+    check(_capi.lib().fhe_b200_sync(batch.stream))
 
 
 class KeySwitchingKey:
@@ -405,11 +478,79 @@ class KeySwitchingKey:
                                               c0.shape[0], C.byref(h)))
         self._h, self.par = h, par
         self.ciphertext_level, self.ksk_level = ciphertext_level, ksk_level
+        self._words = (c0, c1)                   # the caller's key material, for to_bytes (no device read-back entry)
+        # key_switching_key.rs:92-97: a key level with one modulus decomposes in base 2^(log_modulus / 2)
+        self.log_base = ((int(par.moduli()[0]) - 1).bit_length() // 2) if c0.shape[1] == 1 else 0
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
             _release("fhe_b200_ksk_free", h)
+
+    # -- protobuf message (keys/key_switching_key.rs:365-482)
+    def to_bytes(self) -> bytes:
+        """KeySwitchingKeyProto::from(&ksk).encode_to_vec(), unseeded branch: every c0_i and c1_i as an Rq with
+        representation NTTSHOUP (its coefficients are the power-basis words, packed on the device)."""
+        c0, c1 = self._words
+        par, nd = self.par, c0.shape[0]
+        tmp = Ciphertext.from_host(par, np.ascontiguousarray(np.stack([c0, c1], axis=1)), self.ksk_level, NTT)
+        blobs = tmp.to_packed()
+        tmp.sync()
+        deg = par.degree()
+        enc = [[wire.encode_rq(wire.REP_NTTSHOUP, deg, memoryview(blobs[i, j])) for i in range(nd)] for j in range(2)]
+        return wire.encode_ksk(enc[0], enc[1], b"", self.ciphertext_level, self.ksk_level, self.log_base)
+
+    @staticmethod
+    def from_bytes(par: "BfvParameters", data: bytes, seeded_c1: Optional[np.ndarray] = None) -> "KeySwitchingKey":
+        """KeySwitchingKey::try_convert_from(&KeySwitchingKeyProto, par) (key_switching_key.rs:388-482).  A key whose
+        c1 row travels as a seed needs `seeded_c1`: [digits][limbs][N] NTT words of generate_c1 (:130-146), expanded by
+        the Rust host."""
+        k = wire.decode_ksk(data)
+        ct_level, ksk_level, log_base = k["ciphertext_level"], k["ksk_level"], k["log_base"]
+        for lv in (ksk_level, ct_level):
+            if lv > par.max_level():
+                raise WireError("InvalidLevel", _capi.INVALID_LEVEL, "level %d, max %d" % (lv, par.max_level()))
+        if log_base != 0:
+            if ksk_level != par.max_level() or ct_level != par.max_level():
+                raise WireError("InvalidKeySwitchingDecompositionLevels", _capi.INVALID_LEVEL)
+            # as coded (:406-408): the first modulus of the parameter set sizes the decomposition
+            log_modulus = (int(par.moduli()[0]) - 1).bit_length()
+            c0_size = -(-log_modulus // log_base)
+        else:
+            c0_size = len(par.moduli()) - ct_level
+        if len(k["c0"]) != c0_size:
+            raise WireError("WrongPolynomialCount", _capi.BAD_POLY_COUNT,
+                            "KeySwitchingKeyC0: expected %d, found %d" % (c0_size, len(k["c0"])))
+        seed = k["seed"]
+        if not seed:
+            if len(k["c1"]) != c0_size:
+                raise WireError("WrongPolynomialCount", _capi.BAD_POLY_COUNT,
+                                "KeySwitchingKeyC1: expected %d, found %d" % (c0_size, len(k["c1"])))
+            tmp = Ciphertext(par, c0_size, 2, ksk_level, NTT)
+            _unpack_rq(tmp, list(zip(k["c0"], k["c1"])), wire.REP_NTTSHOUP)
+            words = tmp.to_host()
+            tmp.sync()
+            c0, c1 = np.ascontiguousarray(words[:, 0]), np.ascontiguousarray(words[:, 1])
+        else:
+            if len(seed) != 32:
+                raise WireError("InvalidKeySwitchingSeedLength", detail="%d bytes, expected 32" % len(seed))
+            if seeded_c1 is None:
+                raise WireError("SeedExpansion", _capi.UNSUPPORTED,
+                                "the key carries a seed: pass the host-expanded c1 row (key_switching_key.rs:130-146)")
+            tmp = Ciphertext(par, c0_size, 1, ksk_level, NTT)
+            _unpack_rq(tmp, [(m,) for m in k["c0"]], wire.REP_NTTSHOUP)
+            c0 = np.ascontiguousarray(tmp.to_host()[:, 0])
+            tmp.sync()
+            c1 = np.ascontiguousarray(seeded_c1, dtype=np.uint64)
+            if c1.shape != c0.shape:
+                raise FheError(_capi.INVALID_ARGUMENT, "expected seeded_c1 as [digits][limbs][N]")
+        key = KeySwitchingKey(par, c0, c1, ct_level, ksk_level)
+        if key.log_base != log_base:
+            # the reference would compute with whatever base the message names; the device derives the base from the
+            # key level (fhe_b200_ksk_upload), so a message that disagrees is refused rather than reinterpreted
+            raise WireError("InvalidKeySwitchingDecompositionLevels", _capi.UNSUPPORTED,
+                            "log_base %d does not match the key level (expected %d)" % (log_base, key.log_base))
+        return key
 
     @staticmethod
     def from_arrays(par: BfvParameters, c0, c1, ciphertext_level: int = 0, key_level: int = 0) -> "KeySwitchingKey":
@@ -436,6 +577,18 @@ class RGSWCiphertext:
     def from_arrays(par: BfvParameters, k0c0, k0c1, k1c0, k1c1, level: int = 0) -> "RGSWCiphertext":
         return RGSWCiphertext(KeySwitchingKey(par, k0c0, k0c1, level, level), KeySwitchingKey(par, k1c0, k1c1, level, level))
 
+    def to_bytes(self) -> bytes:  # rgsw_ciphertext.rs:30-37
+        return wire.encode_rgsw(self.ksk0.to_bytes(), self.ksk1.to_bytes())
+
+    @staticmethod
+    def from_bytes(par: BfvParameters, data: bytes) -> "RGSWCiphertext":  # rgsw_ciphertext.rs:39-71
+        m0, m1 = wire.decode_rgsw(data)
+        k0, k1 = KeySwitchingKey.from_bytes(par, m0), KeySwitchingKey.from_bytes(par, m1)
+        if k0.ksk_level != k0.ciphertext_level or k0.ciphertext_level != k1.ciphertext_level \
+                or k1.ciphertext_level != k1.ksk_level:
+            raise WireError("InconsistentKeySwitchingLevels", _capi.INVALID_LEVEL)
+        return RGSWCiphertext(k0, k1)
+
     def external_product(self, ct: Ciphertext) -> Ciphertext:
         """&Ciphertext * &RGSWCiphertext (rgsw_ciphertext.rs:122-155): key-switch both parts, add."""
         if ct.level != self.ksk0.ciphertext_level:
@@ -458,6 +611,13 @@ class RelinearizationKey:
     def from_arrays(par: BfvParameters, c0, c1, ciphertext_level: int = 0, key_level: int = 0):
         return RelinearizationKey(KeySwitchingKey(par, c0, c1, ciphertext_level, key_level))
 
+    def to_bytes(self) -> bytes:  # relinearization_key.rs:113-119, :137-141
+        return wire.encode_relinearization_key(self.ksk.to_bytes())
+
+    @staticmethod
+    def from_bytes(par: BfvParameters, data: bytes) -> "RelinearizationKey":  # relinearization_key.rs:121-135
+        return RelinearizationKey(KeySwitchingKey.from_bytes(par, wire.decode_relinearization_key(data)))
+
     def relinearizes(self, ct: Ciphertext) -> Ciphertext:
         """RelinearizationKey::relinearizes (relinearization_key.rs:70-103): (c0,c1,c2) -> (c0,c1).
         (The reference mutates `ct`; a device batch changes shape, so the result is returned.)"""
@@ -475,6 +635,18 @@ class GaloisKey:
     @staticmethod
     def from_arrays(par: BfvParameters, exponent: int, c0, c1, ciphertext_level: int = 0, key_level: int = 0):
         return GaloisKey(exponent, KeySwitchingKey(par, c0, c1, ciphertext_level, key_level))
+
+    def to_bytes(self) -> bytes:  # galois_key.rs:146-153
+        return wire.encode_galois_key(self.ksk.to_bytes(), self.exponent)
+
+    @staticmethod
+    def from_bytes(par: BfvParameters, data: bytes) -> "GaloisKey":  # galois_key.rs:155-173
+        msg, exponent = wire.decode_galois_key(data)
+        ksk = KeySwitchingKey.from_bytes(par, msg)
+        exponent %= 2 * par.degree()            # SubstitutionExponent::new (rq/mod.rs:99-106)
+        if exponent & 1 == 0:
+            raise WireError("InvalidSubstitutionExponent", _capi.INVALID_EXPONENT, str(exponent))
+        return GaloisKey(exponent, ksk)
 
     def relinearize(self, ct: Ciphertext) -> Ciphertext:
         """GaloisKey::relinearize (galois_key.rs:63-86)."""

@@ -1210,15 +1210,17 @@ int fhe_b200_substitute(const fhe_b200_batch* in, uint32_t exponent, fhe_b200_ba
   REQUIRE(in && out && in != out, FHE_B200_INVALID_ARGUMENT, "null or aliased argument");
   check_same(in, out);
   REQUIRE(in->parts == out->parts && in->count == out->count, FHE_B200_BAD_POLY_COUNT, "shapes differ");
-  need_repr(in, FHE_B200_NTT);
   const fhe_b200_params* par = in->par;
   exponent %= 2 * par->N;
   REQUIRE(exponent & 1, FHE_B200_INVALID_EXPONENT, "InvalidSubstitutionExponent");
   DeviceGuard g(par);
-  launch_gather(in->d, out->d, (size_t)in->count * in->parts * in->limbs, par->perm(exponent), par->logn,
-                (cudaStream_t)stream);
+  const size_t rows = (size_t)in->count * in->parts * in->limbs;
+  if (in->repr == FHE_B200_NTT)   // rq/mod.rs:360-389: a permutation of the bit-reversed evaluation points
+    launch_gather(in->d, out->d, rows, par->perm(exponent), par->logn, (cudaStream_t)stream);
+  else                            // rq/mod.rs:390-408: a signed permutation of the coefficients
+    launch_substitute_power(in->d, out->d, rows, exponent, ids_of(in), par->d_limbs, par->logn, (cudaStream_t)stream);
   FHE_CUDA(cudaGetLastError());
-  out->repr = FHE_B200_NTT;
+  out->repr = in->repr;
   API_END
 }
 

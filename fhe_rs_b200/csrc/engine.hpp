@@ -112,6 +112,9 @@ void launch_decompose(const u64* in, u64* out, size_t polys, u32 n_dig, u32 log_
 
 // NTT-domain substitution gather (rq/mod.rs:368-377): out[row][t] = in[row][perm[t]]
 void launch_gather(const u64* in, u64* out, size_t n_rows, const int* perm, u32 logn, cudaStream_t st);
+// Poly<PowerBasis>::substitute (rq/mod.rs:390-408): signed coefficient scatter x^j -> x^(j*exponent)
+void launch_substitute_power(const u64* in, u64* out, size_t n_rows, u32 exponent, const RowIds& ids,
+                             const LimbDev* limbs, u32 logn, cudaStream_t st);
 
 // Poly<PowerBasis>::switch_down (rq/mod.rs:433-492): in [polys][L][N] -> out [polys][L-1][N]
 struct SwitchDownDev {

@@ -875,6 +875,29 @@ __global__ void gather_kernel(const u64* in, u64* out, size_t n_words, const int
   out[i] = in[(row << logn) + perm[t]];
 }
 
+// Poly::substitute, PowerBasis branch (rq/mod.rs:390-408): coefficient j of x^j moves to x^(j*e mod 2N), i.e. to slot
+// (j*e) & (N-1), negated when bit N of j*e is set (x^N = -1).  e is odd, so the map is a bijection: a scatter in which
+// every output word is written exactly once (reads coalesced, writes strided by e).
+struct SubstPowerArgs {
+  const u64* in;
+  u64* out;
+  size_t n_words;
+  u32 logn, limbs_per_poly, exponent;
+  const LimbDev* limbs;
+  unsigned short ids[kMaxPos];
+};
+__global__ void substitute_power_kernel(SubstPowerArgs A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_words) return;
+  const u32 N = 1u << A.logn;
+  const size_t row = i >> A.logn;
+  const u32 j = (u32)i & (N - 1);
+  const u64 p = A.limbs[A.ids[row % A.limbs_per_poly]].p;
+  const u32 power = j * A.exponent;          // mod 2^32 keeps the low logn+1 bits exact
+  const u64 v = A.in[i];
+  A.out[(row << A.logn) + (power & (N - 1))] = (power & N) ? csub(p - v, p) : v;   // Modulus::sub(0, v) / add(0, v)
+}
+
 struct SwitchDownArgs {
   SwitchDownDev S;
   const u64* in;
@@ -1190,6 +1213,17 @@ void launch_gather(const u64* in, u64* out, size_t n_rows, const int* perm, u32 
   size_t n = n_rows << logn;
   if (!n) return;
   gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, perm, logn);
+  g_launches++;
+}
+
+void launch_substitute_power(const u64* in, u64* out, size_t n_rows, u32 exponent, const RowIds& ids,
+                             const LimbDev* limbs, u32 logn, cudaStream_t st) {
+  SubstPowerArgs A;
+  A.in = in; A.out = out; A.n_words = n_rows << logn; A.logn = logn; A.limbs_per_poly = ids.limbs_per_poly;
+  A.exponent = exponent; A.limbs = limbs;
+  copy_ids(A.ids, ids);
+  if (!A.n_words) return;
+  substitute_power_kernel<<<(unsigned)((A.n_words + 255) / 256), 256, 0, st>>>(A);
   g_launches++;
 }
 

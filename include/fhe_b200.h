@@ -189,7 +189,9 @@ int fhe_b200_multiplicator_multiply(const fhe_b200_multiplicator* m, const fhe_b
  * (column rotation by i <-> 3^i mod 2N, row swap <-> 2N-1; evaluation_key.rs:118, :278-286) */
 int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_ksk* gk,
                     fhe_b200_batch* out, void* stream);
-/* Poly::substitute on every row of an NTT batch (rq/mod.rs:360-389) */
+/* Poly::substitute on every row of a batch: the slot permutation of an NTT batch (rq/mod.rs:360-389) or the signed
+ * coefficient permutation x^j -> x^(j*exponent) of a power-basis batch (rq/mod.rs:390-408); `out` takes `in`'s
+ * representation.  Even exponents: FHE_B200_INVALID_EXPONENT. */
 int fhe_b200_substitute(const fhe_b200_batch* in, uint32_t exponent, fhe_b200_batch* out, void* stream);
 /* Ciphertext::switch_down: drop the last modulus with rounding (ciphertext.rs:148-161, rq/mod.rs:433-492).
  * Stream-ordered and in place: the batch keeps its allocation (fhe_b200_batch_device_ptr stays valid, the words of the

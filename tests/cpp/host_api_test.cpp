@@ -1,14 +1,41 @@
 // C++ host-API smoke test: drives the engine through include/fhe_b200.hpp (i.e. through the C ABI) and checks
 // size-independent properties on the GPU: NTT-domain linearity of add/sub/neg, (a*b) relinearized twice gives
 // identical results, and the error behaviour of Multiplicator::multiply (ops/mul.rs:168-189).
-// Built and run by tests/test_gpu_cpp_host.py.   usage: host_api_test <degree> <n_moduli>
+// With a third argument (a directory prepared by the test from the CPU oracle) it also consumes the reference's
+// protobuf messages through include/fhe_b200_wire.hpp -- ciphertexts, a relinearization key, a Galois key -- and writes
+// back words and messages for the test to compare with the oracle's.
+// Built and run by tests/test_gpu_cpp_host.py.   usage: host_api_test <degree> <n_moduli> [<message dir>]
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <iterator>
 #include <random>
 
 #include "fhe_b200.hpp"
+#include "fhe_b200_wire.hpp"
 
 using namespace fhe_b200::bfv;
+
+static std::vector<std::string> read_records(const std::string& path) {   // u32 length + bytes, repeated
+  std::ifstream in(path, std::ios::binary);
+  std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  std::vector<std::string> out;
+  for (size_t pos = 0; pos + 4 <= data.size();) {
+    uint32_t n;
+    memcpy(&n, &data[pos], 4);
+    out.push_back(data.substr(pos + 4, n));
+    pos += 4 + n;
+  }
+  return out;
+}
+static void write_records(const std::string& path, const std::vector<std::string>& recs) {
+  std::ofstream out(path, std::ios::binary);
+  for (auto& r : recs) {
+    uint32_t n = (uint32_t)r.size();
+    out.write((const char*)&n, 4);
+    out.write(r.data(), n);
+  }
+}
 
 int main(int argc, char** argv) {
   const uint32_t degree = argc > 1 ? (uint32_t)atoi(argv[1]) : 64, nmod = argc > 2 ? (uint32_t)atoi(argv[2]) : 3;
@@ -94,6 +121,41 @@ int main(int argc, char** argv) {
       X.sync();
       for (size_t i = 0; i < wa.size(); i++)
         if (down.data()[i] != wa[i]) { printf("FAIL pinned round trip\n"); return 1; }
+    }
+    // protobuf messages: round trip of the batch, then the oracle's messages if the test supplied them
+    {
+      auto msgs = to_bytes(A);
+      if (ciphertext_from_bytes(par, msgs).to_host() != wa) { printf("FAIL message round trip\n"); return 1; }
+      if (to_bytes(ciphertext_from_bytes(par, msgs)) != msgs) { printf("FAIL message bytes not stable\n"); return 1; }
+      try {
+        ciphertext_from_bytes(par, {msgs[0].substr(0, msgs[0].size() - 3)});
+        printf("FAIL expected Decode\n");
+        return 1;
+      } catch (const fhe_b200::WireError& e) {
+        if (e.variant != "Decode") { printf("FAIL wrong variant %s\n", e.variant.c_str()); return 1; }
+      }
+    }
+    if (argc > 3) {
+      const std::string dir = argv[3];
+      auto X = ciphertext_from_bytes(par, read_records(dir + "/cts.bin"));
+      auto xw = X.to_host();
+      std::ofstream(dir + "/out_words.bin", std::ios::binary).write((const char*)xw.data(), (std::streamsize)(xw.size() * 8));
+      write_records(dir + "/out_msgs.bin", to_bytes(X));
+      auto ork = relinearization_key_from_bytes(par, read_records(dir + "/relin.bin")[0]);
+      auto ogk = galois_key_from_bytes(par, read_records(dir + "/galois.bin")[0]);
+      write_records(dir + "/out_mul.bin", to_bytes(Multiplicator::default_(ork).multiply(X, X)));
+      write_records(dir + "/out_rot.bin", to_bytes(ogk.relinearize(X)));
+      // seeded form of the same ciphertexts: the host supplies the expanded halves
+      auto halves = read_records(dir + "/halves.bin")[0];
+      auto S = ciphertext_from_bytes(par, read_records(dir + "/cts_seeded.bin"), (const uint64_t*)halves.data());
+      if (S.to_host() != xw) { printf("FAIL seeded messages\n"); return 1; }
+      try {
+        ciphertext_from_bytes(par, read_records(dir + "/cts_seeded.bin"));
+        printf("FAIL expected SeedExpansion\n");
+        return 1;
+      } catch (const fhe_b200::WireError& e) {
+        if (e.variant != "SeedExpansion" || e.code != FHE_B200_UNSUPPORTED) { printf("FAIL wrong seeded error\n"); return 1; }
+      }
     }
     // error behaviour
     try {

@@ -312,6 +312,16 @@ def test_galois_and_key_switch(oracle, F, degree, nmod):
     with pytest.raises(F.FheError) as err:
         X.substitute(4)
     assert err.value.code == -10
+    # the PowerBasis branch (rq/mod.rs:390-408): signed coefficient permutation; substitution commutes with the NTT
+    PB = X.clone().into_power_basis()
+    for e in exps + (2 * degree + 3,):
+        sub = PB.substitute(e)
+        assert sub.representation == F.POWER_BASIS
+        got = sub.to_host()
+        for i in range(count):
+            for p in range(2):
+                assert (got[i, p] == octs[i].c[p].copy().into_power_basis().substitute(e).c).all()
+        assert (sub.into_ntt().to_host() == X.substitute(e).to_host()).all()
     # EvaluationKey rotations decrypt to the expected slot permutation
     ek = F.EvaluationKey(gpar)
     for e in exps:
@@ -882,3 +892,112 @@ def test_mixed_sizes_through_tma_kernels(oracle, F):
     R = F.GaloisKey.from_arrays(gpar, 3, gc[0], gc[1]).relinearize(A).to_host()
     for i in (0, count - 1):
         assert (R[i] == ogk.relinearize(oracle.Ciphertext.from_array(opar, a[i], 0)).to_array()).all()
+
+
+@pytest.mark.parametrize("degree,nmod", [(16, 6), (64, 3), (8192, 2)])
+def test_messages_against_oracle(oracle, F, degree, nmod):
+    """The protobuf messages either side of the path (SURVEY 8f row 1): `Ciphertext::{to_bytes, from_bytes}`
+    (bfv/ciphertext.rs:230-317), key-switching / relinearization / Galois keys and RGSW ciphertexts
+    (keys/key_switching_key.rs:365-482, relinearization_key.rs:113-141, galois_key.rs:146-173,
+    rgsw_ciphertext.rs:30-71): bytes produced by the oracle are consumed by the device path and give the oracle's
+    words and results; bytes produced by the device path are the oracle's bytes."""
+    import fhe_wire as ow
+    t = 65537
+    opar, gpar, rng = make_pair(oracle, F, degree, nmod, t, 300 + degree)
+    sk = oracle.SecretKey(opar, rng)
+    last = nmod - 1
+
+    cts = [sk.encrypt(rng.integers(0, t, degree), 0, rng) for _ in range(3)]
+    for batch in (cts, [c.mul(c) for c in cts[:2]], [c.copy().switch_to_level(1) for c in cts]):
+        msgs = [ow.ciphertext_to_bytes(c) for c in batch]
+        G = F.Ciphertext.from_bytes(gpar, msgs)
+        assert G.level == batch[0].level and len(G) == len(batch[0].c)
+        assert (G.to_host() == np.stack([c.to_array() for c in batch])).all()
+        assert G.to_bytes() == msgs
+    # seeded ciphertexts: the last polynomial travels as a seed and is expanded by the host
+    seeded = [ow.ciphertext_to_bytes(c, seed=bytes([i]) * 32) for i, c in enumerate(cts)]
+    G = F.Ciphertext.from_bytes(gpar, seeded, seeded_halves=np.stack([c.c[1].c for c in cts]))
+    assert (G.to_host() == np.stack([c.to_array() for c in cts])).all()
+    with pytest.raises(F.WireError) as e:
+        F.Ciphertext.from_bytes(gpar, seeded)
+    assert e.value.variant == "SeedExpansion" and e.value.code == -11
+
+    # keys from their messages: the results of the path are the oracle's
+    ork = oracle.RelinearizationKey(sk, rng)
+    ogk = oracle.GaloisKey(sk, 3, rng)
+    grk = F.RelinearizationKey.from_bytes(gpar, ow.relin_key_to_bytes(ork))
+    ggk = F.GaloisKey.from_bytes(gpar, ow.galois_key_to_bytes(ogk))
+    assert grk.to_bytes() == ow.relin_key_to_bytes(ork) and ggk.to_bytes() == ow.galois_key_to_bytes(ogk)
+    A = F.Ciphertext.from_bytes(gpar, [ow.ciphertext_to_bytes(c) for c in cts[:2]])
+    B = F.Ciphertext.from_bytes(gpar, [ow.ciphertext_to_bytes(c) for c in cts[1:]])
+    out = F.Multiplicator.default(grk).multiply(A, B)
+    om = oracle.Multiplicator.default(ork)
+    assert out.to_bytes() == [ow.ciphertext_to_bytes(om.multiply(cts[i], cts[i + 1])) for i in range(2)]
+    assert ggk.relinearize(A).to_bytes() == [ow.ciphertext_to_bytes(ogk.relinearize(c)) for c in cts[:2]]
+    # a seeded key: c1 row from the host
+    seeded_key = ow.ksk_to_bytes(ork.ksk, seed=b"k" * 32)
+    k2 = F.KeySwitchingKey.from_bytes(gpar, seeded_key, seeded_c1=np.stack([p.c for p in ork.ksk.c1]))
+    assert k2.to_bytes() == ow.ksk_to_bytes(ork.ksk)
+    # the last level has one modulus: base-2^31 digits (key_switching_key.rs:92-110, :401-409), RGSW at that level
+    m = oracle.Poly.random(opar.context_at_level(last), oracle.NTT, rng)
+    org = oracle.RGSWCiphertext(sk, m, last, rng)
+    grg = F.RGSWCiphertext.from_bytes(gpar, ow.rgsw_to_bytes(org))
+    assert grg.to_bytes() == ow.rgsw_to_bytes(org)
+    low = cts[0].copy().switch_to_level(last)
+    got = grg.external_product(F.Ciphertext.from_bytes(gpar, [ow.ciphertext_to_bytes(low)]))
+    assert got.to_bytes() == [ow.ciphertext_to_bytes(org.external_product(low))]
+
+    # rejections carry the reference's variant names (the oracle raises the same ones on the same bytes)
+    def both(variant, data, gpu_call, oracle_call):
+        with pytest.raises(F.WireError) as e:
+            gpu_call(data)
+        assert e.value.variant == variant
+        with pytest.raises(ow.WireError, match=variant):
+            oracle_call(data)
+
+    good = ow.CiphertextProto()
+    good.ParseFromString(ow.ciphertext_to_bytes(cts[0]))
+    rq = ow.Rq()
+    rq.ParseFromString(good.c[0])
+    for change, variant in ((dict(representation=0), "UnknownRepresentation"), (dict(representation=1), "RepresentationMismatch"),
+                            (dict(degree=6), "InvalidDegree"), (dict(coefficients=rq.coefficients[:-1]), "InvalidCoefficientCount"),
+                            (dict(degree=degree * 2), "InvalidCoefficientCount")):
+        bad_rq = ow.Rq()
+        bad_rq.CopyFrom(rq)
+        for k, v in change.items():
+            setattr(bad_rq, k, v)
+        bad = ow.CiphertextProto()
+        bad.CopyFrom(good)
+        bad.c[0] = bad_rq.SerializeToString()
+        both(variant, bad.SerializeToString(), lambda d: F.Ciphertext.from_bytes(gpar, [d]),
+             lambda d: ow.ciphertext_from_bytes(opar, d))
+    bad = ow.CiphertextProto()
+    bad.CopyFrom(good)
+    bad.level = nmod
+    both("InvalidLevel", bad.SerializeToString(), lambda d: F.Ciphertext.from_bytes(gpar, [d]),
+         lambda d: ow.ciphertext_from_bytes(opar, d))
+    both("InvalidCiphertextPolynomialCount", ow.CiphertextProto(c=[good.c[0]]).SerializeToString(),
+         lambda d: F.Ciphertext.from_bytes(gpar, [d]), lambda d: ow.ciphertext_from_bytes(opar, d))
+    both("Decode", ow.ciphertext_to_bytes(cts[0])[:-5], lambda d: F.Ciphertext.from_bytes(gpar, [d]),
+         lambda d: ow.ciphertext_from_bytes(opar, d))
+    key = ow.KeySwitchingKeyProto()
+    key.ParseFromString(ow.ksk_to_bytes(ork.ksk))
+    del key.c0[-1]
+    both("WrongPolynomialCount", key.SerializeToString(), lambda d: F.KeySwitchingKey.from_bytes(gpar, d),
+         lambda d: ow.ksk_from_bytes(opar, d))
+    key.ParseFromString(ow.ksk_to_bytes(ork.ksk))
+    key.log_base = 31
+    both("InvalidKeySwitchingDecompositionLevels", key.SerializeToString(), lambda d: F.KeySwitchingKey.from_bytes(gpar, d),
+         lambda d: ow.ksk_from_bytes(opar, d))
+    gal = ow.GaloisKeyProto()
+    gal.ParseFromString(ow.galois_key_to_bytes(ogk))
+    gal.exponent = 2 * degree + 4
+    both("InvalidSubstitutionExponent", gal.SerializeToString(), lambda d: F.GaloisKey.from_bytes(gpar, d),
+         lambda d: ow.galois_key_from_bytes(opar, d))
+    both("MissingField", b"", lambda d: F.RelinearizationKey.from_bytes(gpar, d), lambda d: ow.relin_key_from_bytes(opar, d))
+    if degree == 16:   # one modulus: a shorter polynomial is a low-order one, zero-extended (rq/convert.rs:160-183)
+        ctx8 = oracle.Context(opar.moduli[:1], 8)
+        short = [oracle.Poly.random(ctx8, oracle.NTT, rng) for _ in range(2)]
+        data = ow.CiphertextProto(c=[ow.poly_to_bytes(p) for p in short], level=last).SerializeToString()
+        got = F.Ciphertext.from_bytes(gpar, [data])
+        assert (got.to_host()[0] == ow.ciphertext_from_bytes(opar, data).to_array()).all()

@@ -1,0 +1,321 @@
+"""CPU tests of the message layer either side of the path.
+
+ * `fhe_rs_b200/wire.py` (hand-written proto3 framing, host logic of the product) against the google.protobuf
+   runtime, byte for byte, on the reference's schema (rq.proto:5-17, bfv.proto:5-32);
+ * the oracle's message functions (`oracle/fhe_wire.py`) on the reference's own round-trip and rejection tests:
+   rq/serialize.rs:49-155, bfv/ciphertext.rs:332-372, keys/key_switching_key.rs:629-652,
+   keys/relinearization_key.rs:276-, keys/galois_key.rs:280-, bfv/rgsw_ciphertext.rs:225-.
+The device half (pack / unpack of the coefficients) is covered by the `-m gpu` tests."""
+import os
+
+import numpy as np
+import pytest
+
+from fhe_rs_b200 import wire
+from fhe_rs_b200.wire import WireError
+
+
+@pytest.fixture(scope="module")
+def ow(oracle):
+    import fhe_wire
+    return fhe_wire
+
+
+def _rand_bytes(rng, n):
+    return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+
+
+def test_codec_matches_protobuf_runtime(ow):
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        rep = int(rng.integers(0, 4))
+        degree = int(rng.choice([0, 8, 16, 4096, 32768, 1 << 20]))
+        coeffs = _rand_bytes(rng, int(rng.choice([0, 1, 127, 128, 300, 20000])))
+        m = ow.Rq(representation=rep, degree=degree, coefficients=coeffs)
+        assert wire.encode_rq(rep, degree, coeffs) == m.SerializeToString()
+        assert wire.rq_overhead(degree, len(coeffs), rep) + len(coeffs) == len(m.SerializeToString())
+
+        polys = [_rand_bytes(rng, int(rng.integers(0, 400))) for _ in range(int(rng.integers(0, 4)))]
+        seed = _rand_bytes(rng, 32) if trial % 3 == 0 else b""
+        level = int(rng.integers(0, 5)) if trial % 2 else 0
+        c = ow.CiphertextProto(c=polys, seed=seed, level=level)
+        enc = wire.encode_ciphertext(polys, seed, level)
+        assert enc == c.SerializeToString()
+        if polys and (len(polys) > 1 or seed):
+            got = wire.decode_ciphertext(enc)
+            assert [bytes(x) for x in got[0]] == polys and got[1] == seed and got[2] == level
+
+        c0 = [_rand_bytes(rng, 200) for _ in range(int(rng.integers(0, 4)))]
+        c1 = [_rand_bytes(rng, 129) for _ in range(int(rng.integers(0, 4)))]
+        args = (int(rng.integers(0, 3)), int(rng.integers(0, 3)), int(rng.choice([0, 31])))
+        k = ow.KeySwitchingKeyProto(c0=c0, c1=c1, seed=seed, ciphertext_level=args[0], ksk_level=args[1], log_base=args[2])
+        kb = wire.encode_ksk(c0, c1, seed, *args)
+        assert kb == k.SerializeToString()
+        d = wire.decode_ksk(kb)
+        assert [bytes(x) for x in d["c0"]] == c0 and [bytes(x) for x in d["c1"]] == c1 and d["seed"] == seed
+        assert (d["ciphertext_level"], d["ksk_level"], d["log_base"]) == args
+
+        r = ow.RelinearizationKeyProto(ksk=k)
+        assert wire.encode_relinearization_key(kb) == r.SerializeToString()
+        assert bytes(wire.decode_relinearization_key(r.SerializeToString())) == kb
+        e = int(rng.integers(0, 1 << 17))
+        g = ow.GaloisKeyProto(ksk=k, exponent=e)
+        assert wire.encode_galois_key(kb, e) == g.SerializeToString()
+        gm, ge = wire.decode_galois_key(g.SerializeToString())
+        assert bytes(gm) == kb and ge == e
+        w = ow.RGSWCiphertextProto(ksk0=k, ksk1=k)
+        assert wire.encode_rgsw(kb, kb) == w.SerializeToString()
+        assert [bytes(x) for x in wire.decode_rgsw(w.SerializeToString())] == [kb, kb]
+
+
+def test_codec_accepts_what_prost_accepts_and_rejects_garbage(ow):
+    coeffs = os.urandom(64)
+    canonical = wire.encode_rq(2, 16, coeffs)
+    # any field order, unknown fields (varint / fixed64 / bytes / fixed32) skipped, the last occurrence of a scalar wins
+    shuffled = (b"\x1a" + bytes([len(coeffs)]) + coeffs      # field 3
+                + b"\x78\x05"                                # unknown field 15, varint
+                + b"\x10\x08" + b"\x10\x10"                  # degree 8, then degree 16
+                + b"\x79" + b"\0" * 8                        # unknown field 15, fixed64
+                + b"\x7d" + b"\0" * 4                        # unknown field 15, fixed32
+                + b"\x7a\x02ab"                              # unknown field 15, bytes
+                + b"\x08\x02"                                # representation NTT
+                + b"\x20\x01")                               # allow_variable_time = true: ignored (convert.rs:39-41)
+    rep, degree, c = wire.decode_rq(shuffled)
+    assert (rep, degree, bytes(c)) == (2, 16, coeffs)
+    m = ow.Rq()
+    m.ParseFromString(shuffled)
+    assert (m.representation, m.degree, m.coefficients) == (2, 16, coeffs)
+    assert wire.decode_rq(canonical)[:2] == (2, 16)
+
+    for bad in (b"\x08", b"\x1a\x05ab", b"\x00\x01", b"\x0b", b"\x08" + b"\xff" * 11, b"\x19\x01\x02"):
+        with pytest.raises(WireError) as e:
+            wire.decode_rq(bad)
+        assert e.value.variant == "Decode"
+        with pytest.raises(Exception):
+            ow.Rq().ParseFromString(bad)
+    with pytest.raises(WireError) as e:                  # a known field with the wrong wire type
+        wire.decode_rq(b"\x12\x01a")
+    assert e.value.variant == "Decode"
+
+    # rq/serialize.rs:74-126
+    for kwargs, variant in ((dict(representation=0, degree=16, coefficients=coeffs), "UnknownRepresentation"),
+                            (dict(representation=7, degree=16, coefficients=coeffs), "InvalidRepresentation"),
+                            (dict(representation=1, degree=6, coefficients=coeffs), "InvalidDegree"),
+                            (dict(representation=1, degree=0, coefficients=coeffs), "InvalidDegree")):
+        with pytest.raises(WireError) as e:
+            wire.decode_rq(ow.Rq(**kwargs).SerializeToString())
+        assert e.value.variant == variant
+    # ciphertext.rs:261-269
+    for polys, seed in (([], b""), ([b"x"], b""), ([], b"s" * 32)):
+        with pytest.raises(WireError) as e:
+            wire.decode_ciphertext(wire.encode_ciphertext(polys, seed, 0))
+        assert e.value.variant == "InvalidCiphertextPolynomialCount"
+    for dec, msg, field in ((wire.decode_relinearization_key, b"", "RelinearizationKeySwitchingKey"),
+                            (wire.decode_galois_key, b"\x10\x03", "GaloisKeySwitchingKey"),
+                            (wire.decode_rgsw, b"", "RgswKeySwitchingKey0"),
+                            (wire.decode_rgsw, b"\x0a\x00", "RgswKeySwitchingKey1")):
+        with pytest.raises(WireError) as e:
+            dec(msg)
+        assert e.value.variant == "MissingField" and field in str(e.value)
+
+
+Q3 = [4611686018282684417, 4611686018326724609, 4611686018309947393]   # rq/serialize.rs:43-47
+
+
+def test_oracle_polynomial_messages(oracle, ow):
+    """rq/serialize.rs:49-155"""
+    rng = np.random.default_rng(11)
+    for moduli in ([Q3[0]], [Q3[1]], [Q3[2]], Q3):
+        ctx = oracle.Context(moduli, 16)
+        for rep in (oracle.POWER_BASIS, oracle.NTT, oracle.NTT_SHOUP):
+            p = oracle.Poly.random(ctx, rep, rng)
+            q = ow.poly_from_bytes(ctx, ow.poly_to_bytes(p), rep)
+            assert q.rep == rep and (q.c == p.c).all()
+            # the product's framing of the same polynomial is the same message
+            assert wire.encode_rq({oracle.POWER_BASIS: 1, oracle.NTT: 2, oracle.NTT_SHOUP: 3}[rep], 16,
+                                  oracle.poly_to_rq_coefficients(p)) == ow.poly_to_bytes(p)
+    ctx = oracle.Context(Q3, 16)
+    p = oracle.Poly.random(ctx, oracle.POWER_BASIS, rng)
+    good = ow.Rq()
+    good.ParseFromString(ow.poly_to_bytes(p))
+    for change, variant in ((dict(representation=0), "UnknownRepresentation"), (dict(degree=6), "InvalidDegree"),
+                            (dict(coefficients=b""), "InvalidCoefficientCount"),
+                            (dict(representation=2), "RepresentationMismatch")):
+        m = ow.Rq()
+        m.CopyFrom(good)
+        for k, v in change.items():
+            setattr(m, k, v)
+        with pytest.raises(ow.WireError, match=variant):
+            ow.poly_from_bytes(ctx, m.SerializeToString(), oracle.POWER_BASIS)
+    good.allow_variable_time = True            # serialize.rs:144-155: the flag on the wire is ignored
+    assert (ow.poly_from_bytes(ctx, good.SerializeToString(), oracle.POWER_BASIS).c == p.c).all()
+    with pytest.raises(ow.WireError, match="Decode"):
+        ow.poly_from_bytes(ctx, b"\x08", oracle.POWER_BASIS)
+    # one modulus: a shorter polynomial is a low-order one (convert.rs:160-183)
+    ctx1, ctx8 = oracle.Context(Q3[:1], 16), oracle.Context(Q3[:1], 8)
+    short = oracle.Poly.random(ctx8, oracle.POWER_BASIS, rng)
+    got = ow.poly_from_bytes(ctx1, ow.poly_to_bytes(short), oracle.POWER_BASIS)
+    assert (got.c[0, :8] == short.c[0]).all() and not got.c[0, 8:].any()
+    with pytest.raises(ow.WireError, match="InvalidCoefficientCount"):
+        ow.poly_from_bytes(ctx, ow.poly_to_bytes(oracle.Poly.random(oracle.Context(Q3, 8), oracle.POWER_BASIS, rng)),
+                           oracle.POWER_BASIS)
+
+
+@pytest.mark.parametrize("nmod", [1, 6])
+def test_oracle_ciphertext_messages(oracle, ow, nmod):
+    """bfv/ciphertext.rs:332-372 (`proto_conversion`, `serialize`), fresh and after a product (three parts)"""
+    rng = np.random.default_rng(17 + nmod)
+    par = oracle.BfvParameters(16, 1153, moduli_sizes=[62] * nmod)
+    sk = oracle.SecretKey(par, rng)
+    ct = sk.encrypt(rng.integers(0, 1153, 16), 0, rng)
+    for c in (ct, ct.mul(ct)):
+        back = ow.ciphertext_from_bytes(par, ow.ciphertext_to_bytes(c))
+        assert back.level == c.level and (back.to_array() == c.to_array()).all()
+    # the seeded form: all parts but the last, plus the seed; the expanded half comes from the host
+    seed = bytes(range(32))
+    data = ow.ciphertext_to_bytes(ct, seed=seed)
+    assert len(data) == len(ow.ciphertext_to_bytes(ct)) - len(ow.poly_to_bytes(ct.c[1])) - 3 + 34   # tag + 2-byte length gone, tag + length + 32 seed bytes added
+    back = ow.ciphertext_from_bytes(par, data, seeded_half=ct.c[1].c)
+    assert (back.to_array() == ct.to_array()).all()
+    with pytest.raises(ow.WireError, match="SeedExpansion"):
+        ow.ciphertext_from_bytes(par, data)
+    with pytest.raises(ow.WireError, match="InvalidCiphertextPolynomialCount"):
+        ow.ciphertext_from_bytes(par, ow.CiphertextProto(c=[ow.poly_to_bytes(ct.c[0])]).SerializeToString())
+    with pytest.raises(ow.WireError, match="InvalidLevel"):
+        m = ow.CiphertextProto()
+        m.ParseFromString(ow.ciphertext_to_bytes(ct))
+        m.level = nmod
+        ow.ciphertext_from_bytes(par, m.SerializeToString())
+    if nmod > 1:
+        low = ct.copy().switch_to_level(1)
+        back = ow.ciphertext_from_bytes(par, ow.ciphertext_to_bytes(low))
+        assert back.level == 1 and (back.to_array() == low.to_array()).all()
+
+
+@pytest.mark.parametrize("nmod", [6, 3])
+def test_oracle_key_messages(oracle, ow, nmod):
+    """keys/key_switching_key.rs:629-652, relinearization_key.rs / galois_key.rs / rgsw_ciphertext.rs round trips"""
+    rng = np.random.default_rng(23 + nmod)
+    par = oracle.BfvParameters(16, 1153, moduli_sizes=[62] * nmod)
+    sk = oracle.SecretKey(par, rng)
+    last = nmod - 1
+
+    def same(a, b):
+        assert (a.ciphertext_level, a.ksk_level, a.log_base) == (b.ciphertext_level, b.ksk_level, b.log_base)
+        assert all((x.c == y.c).all() for x, y in zip(a.c0 + a.c1, b.c0 + b.c1)) and len(a.c0) == len(b.c0)
+
+    rk = oracle.RelinearizationKey(sk, rng)
+    same(ow.ksk_from_bytes(par, ow.ksk_to_bytes(rk.ksk)), rk.ksk)
+    same(ow.relin_key_from_bytes(par, ow.relin_key_to_bytes(rk)).ksk, rk.ksk)
+    rk10 = oracle.RelinearizationKey(sk, rng, 1, 0)                 # key one level above the ciphertexts
+    same(ow.relin_key_from_bytes(par, ow.relin_key_to_bytes(rk10)).ksk, rk10.ksk)
+    gk = oracle.GaloisKey(sk, 9, rng)
+    back = ow.galois_key_from_bytes(par, ow.galois_key_to_bytes(gk))
+    assert back.exponent == 9
+    same(back.ksk, gk.ksk)
+    # last level: one modulus, base-2^31 decomposition (key_switching_key.rs:92-110, :401-409)
+    ctx = par.context_at_level(last)
+    m = oracle.Poly.random(ctx, oracle.NTT, rng)
+    rg = oracle.RGSWCiphertext(sk, m, last, rng)
+    assert rg.ksk0.log_base == 31 and len(rg.ksk0.c0) == 2
+    back = ow.rgsw_from_bytes(par, ow.rgsw_to_bytes(rg))
+    same(back.ksk0, rg.ksk0)
+    same(back.ksk1, rg.ksk1)
+
+    msg = ow.KeySwitchingKeyProto()
+    msg.ParseFromString(ow.ksk_to_bytes(rk.ksk))
+    bad = ow.KeySwitchingKeyProto()
+    bad.CopyFrom(msg)
+    del bad.c0[-1]
+    with pytest.raises(ow.WireError, match="WrongPolynomialCount:KeySwitchingKeyC0"):
+        ow.ksk_from_bytes(par, bad.SerializeToString())
+    bad.CopyFrom(msg)
+    del bad.c1[0]
+    with pytest.raises(ow.WireError, match="WrongPolynomialCount:KeySwitchingKeyC1"):
+        ow.ksk_from_bytes(par, bad.SerializeToString())
+    bad.CopyFrom(msg)
+    bad.log_base = 31                                               # a decomposition key above the last level
+    with pytest.raises(ow.WireError, match="InvalidKeySwitchingDecompositionLevels"):
+        ow.ksk_from_bytes(par, bad.SerializeToString())
+    bad.CopyFrom(msg)
+    del bad.c1[:]
+    bad.seed = b"s" * 31
+    with pytest.raises(ow.WireError, match="InvalidKeySwitchingSeedLength"):
+        ow.ksk_from_bytes(par, bad.SerializeToString())
+    bad.seed = b"s" * 32                                            # seeded key: c1 row supplied by the host
+    same(ow.ksk_from_bytes(par, bad.SerializeToString(), seeded_c1=[p.c for p in rk.ksk.c1]), rk.ksk)
+    with pytest.raises(ow.WireError, match="MissingField"):
+        ow.relin_key_from_bytes(par, b"")
+    g = ow.GaloisKeyProto()
+    g.ParseFromString(ow.galois_key_to_bytes(gk))
+    g.exponent = 4
+    with pytest.raises(ow.WireError, match="InvalidSubstitutionExponent"):
+        ow.galois_key_from_bytes(par, g.SerializeToString())
+    w = ow.RGSWCiphertextProto()
+    w.ksk0.CopyFrom(msg)
+    w.ksk1.ParseFromString(ow.ksk_to_bytes(rk10.ksk))
+    with pytest.raises(ow.WireError, match="InconsistentKeySwitchingLevels"):
+        ow.rgsw_from_bytes(par, w.SerializeToString())
+
+
+def test_cpp_codec_matches_protobuf_runtime(ow, tmp_path):
+    """include/fhe_b200_wire.hpp (the C++ host's codec): decode + canonical re-encode of shuffled / padded messages
+    must give the google.protobuf runtime's bytes; malformed input is refused with the reference's variant names"""
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "wire_codec_test")
+    lib_dir = os.path.join(root, "fhe_rs_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "wire_codec_test.cpp"), "-o", exe,
+                           "-L", lib_dir, "-lfhe_b200", "-Wl,-rpath," + lib_dir])
+    rng = np.random.default_rng(9)
+    records, expect = [], []
+    unknown = b"\x78\x05" + b"\x7a\x02ab" + b"\x79" + b"\0" * 8     # field 15: varint, bytes, fixed64
+
+    def add(kind, data, want):
+        records.append(kind.encode() + struct.pack("<I", len(data)) + data)
+        expect.append(want)
+
+    for trial in range(40):
+        coeffs = _rand_bytes(rng, int(rng.choice([0, 1, 127, 128, 300, 20000])))
+        m = ow.Rq(representation=int(rng.integers(1, 4)), degree=int(rng.choice([8, 16, 4096, 32768])), coefficients=coeffs)
+        add("q", m.SerializeToString(), m.SerializeToString())
+        add("q", unknown + m.SerializeToString() + b"\x20\x01", m.SerializeToString())
+        polys = [_rand_bytes(rng, int(rng.integers(0, 400))) for _ in range(int(rng.integers(2, 4)))]
+        seed = _rand_bytes(rng, 32) if trial % 3 == 0 else b""
+        c = ow.CiphertextProto(c=polys, seed=seed, level=int(rng.integers(0, 5)))
+        add("c", c.SerializeToString(), c.SerializeToString())
+        # fields out of order: level first, then the polynomials
+        add("c", wire.encode_ciphertext([], b"", c.level) + unknown + wire.encode_ciphertext(polys, seed, 0), c.SerializeToString())
+        k = ow.KeySwitchingKeyProto(c0=[_rand_bytes(rng, 200) for _ in range(3)], c1=[_rand_bytes(rng, 129) for _ in range(3)],
+                                    seed=seed, ciphertext_level=int(rng.integers(0, 3)), ksk_level=int(rng.integers(0, 3)),
+                                    log_base=int(rng.choice([0, 31])))
+        add("k", k.SerializeToString(), k.SerializeToString())
+        add("r", ow.RelinearizationKeyProto(ksk=k).SerializeToString(), ow.RelinearizationKeyProto(ksk=k).SerializeToString())
+        g = ow.GaloisKeyProto(ksk=k, exponent=int(rng.integers(0, 1 << 17)))
+        add("g", g.SerializeToString(), g.SerializeToString())
+    for data, variant in ((b"\x08", "Decode"), (b"\x1a\x05ab", "Decode"), (b"\x00\x01", "Decode"), (b"\x0b", "Decode"),
+                          (b"\x12\x01a", "Decode"), (ow.Rq(degree=16).SerializeToString(), "UnknownRepresentation"),
+                          (ow.Rq(representation=9, degree=16).SerializeToString(), "InvalidRepresentation"),
+                          (ow.Rq(representation=1, degree=6).SerializeToString(), "InvalidDegree")):
+        add("q", data, variant)
+    add("c", ow.CiphertextProto(c=[b"x"]).SerializeToString(), "InvalidCiphertextPolynomialCount")
+    add("r", b"", "MissingField")
+    add("g", b"\x10\x03", "MissingField")
+    (tmp_path / "in.bin").write_bytes(b"".join(records))
+    subprocess.check_call([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out = (tmp_path / "out.bin").read_bytes()
+    pos = 0
+    for want in expect:
+        (n,) = struct.unpack_from("<I", out, pos)
+        pos += 4
+        if n == 0xFFFFFFFF:
+            (n,) = struct.unpack_from("<I", out, pos)
+            pos += 4
+            got = out[pos:pos + n].decode()
+        else:
+            got = out[pos:pos + n]
+        pos += n
+        assert got == want
+    assert pos == len(out)
