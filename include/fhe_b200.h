@@ -214,7 +214,8 @@ int fhe_b200_batch_alloc_mul_basis(const fhe_b200_params* p, uint32_t count, uin
  * `Rq.coefficients` of the reference's protobuf message (fhe-math/src/proto/rq.proto:12-17) is, for every limb
  * in order, the power-basis coefficients bit-packed LSB first with ceil(log2 q_i) bits each
  * (Modulus::serialize_vec zq/mod.rs:783-786, fhe_util::transcode_to_bytes fhe-util/src/lib.rs:71-108).
- * The protobuf framing itself (tags, varints, `representation`, `degree`) stays with the host's prost code. */
+ * The protobuf framing itself (tags, varints, `representation`, `degree`) is host work: a Rust host keeps its prost
+ * code; C++ and Python hosts have the same messages in include/fhe_b200_wire.hpp / fhe_rs_b200/wire.py. */
 /* Seeded ("compact") ciphertexts and keys are NOT expanded here.  The reference serialises a fresh ciphertext as c0 plus
  * the 32-byte seed of c1 (bfv/ciphertext.rs:231-317; keys: key_switching_key.rs:365-482) and regenerates c1 with
  * Poly::random_from_seed (rq/mod.rs:276-292): ChaCha8Rng::from_seed(seed) driving rand's uniform u64 sampling per
