@@ -68,8 +68,13 @@ def _put_len(out: List[Bytes], field: int, payload: Bytes) -> None:
     out.append(payload)
 
 
+_START_GROUP, _END_GROUP = 3, 4
+
+
 def _fields(buf: Bytes) -> Iterator[Tuple[int, int, Union[int, memoryview]]]:
-    """(field number, wire type, value) of one message; raises WireError("Decode") on malformed input"""
+    """(field number, wire type, value) of one message; raises WireError("Decode") on malformed input.  Follows prost's
+    decoder: keys are 32-bit with a field number >= 1, varints are at most ten bytes, unknown groups are skipped whole
+    (they never occur in these messages), an unmatched end-group or wire types 6 / 7 are errors."""
     mv = memoryview(buf).cast("B") if not isinstance(buf, memoryview) else buf.cast("B")
     pos, end = 0, len(mv)
 
@@ -77,36 +82,62 @@ def _fields(buf: Bytes) -> Iterator[Tuple[int, int, Union[int, memoryview]]]:
         nonlocal pos
         shift = value = 0
         while True:
-            if pos >= end or shift > 63:
-                raise WireError("Decode", detail="truncated or overlong varint")
+            if pos >= end:
+                raise WireError("Decode", detail="truncated varint")
             b = mv[pos]
             pos += 1
+            if shift == 63 and b > 1:
+                raise WireError("Decode", detail="varint overflows 64 bits")
             value |= (b & 0x7F) << shift
             if not b & 0x80:
-                return value & 0xFFFFFFFFFFFFFFFF
+                return value
             shift += 7
 
-    while pos < end:
-        key = varint()
-        field, wt = key >> 3, key & 7
-        if field == 0:
+    def key() -> Tuple[int, int]:
+        k = varint()
+        if k > 0xFFFFFFFF:
+            raise WireError("Decode", detail="key does not fit 32 bits")
+        if k >> 3 == 0:
             raise WireError("Decode", detail="field number 0")
+        return k >> 3, k & 7
+
+    def value(field: int, wt: int, depth: int):
+        nonlocal pos
         if wt == _VARINT:
-            yield field, wt, varint()
-        elif wt == _LEN:
+            return varint()
+        if wt == _LEN:
             n = varint()
             if n > end - pos:
                 raise WireError("Decode", detail="length-delimited field overruns the buffer")
-            yield field, wt, mv[pos:pos + n]
             pos += n
-        elif wt == _I64 or wt == _I32:
+            return mv[pos - n:pos]
+        if wt == _I64 or wt == _I32:
             n = 8 if wt == _I64 else 4
             if n > end - pos:
                 raise WireError("Decode", detail="truncated fixed-width field")
-            yield field, wt, int.from_bytes(mv[pos:pos + n], "little")
             pos += n
+            return int.from_bytes(mv[pos - n:pos], "little")
+        if wt == _START_GROUP:
+            if depth >= 100:
+                raise WireError("Decode", detail="recursion limit")
+            while True:
+                if pos >= end:
+                    raise WireError("Decode", detail="unterminated group")
+                f, w = key()
+                if w == _END_GROUP:
+                    if f != field:
+                        raise WireError("Decode", detail="mismatched end of group")
+                    return None
+                value(f, w, depth + 1)
+        raise WireError("Decode", detail="unsupported wire type %d" % wt)
+
+    while pos < end:
+        field, wt = key()
+        v = value(field, wt, 0)
+        if wt != _START_GROUP:
+            yield field, wt, v
         else:
-            raise WireError("Decode", detail="unsupported wire type %d" % wt)
+            yield field, wt, 0
 
 
 def _expect(wt: int, want: int) -> None:

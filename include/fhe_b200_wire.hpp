@@ -59,42 +59,21 @@ inline void put_len(std::string& out, uint32_t field, const void* data, size_t n
 }
 inline void put_len(std::string& out, uint32_t field, const std::string& s) { put_len(out, field, s.data(), s.size()); }
 
-// one message, field by field
+// one message, field by field.  Follows prost's decoder: keys are 32-bit with a field number >= 1, varints are at most
+// ten bytes, unknown groups are skipped whole (they never occur in these messages), an unmatched end-group or wire
+// types 6 / 7 are errors, a known field with another wire type is an error (expect()).
 class Reader {
  public:
   Reader(const void* p, size_t n) : p_((const uint8_t*)p), end_((const uint8_t*)p + n) {}
   // false at the end of the message; otherwise field / wire_type and (varint, fixed) value or (bytes) span
   bool next() {
     if (p_ >= end_) return false;
-    uint64_t key = varint();
-    field = (uint32_t)(key >> 3);
-    wire_type = (int)(key & 7);
-    if (field == 0) throw WireError("Decode", FHE_B200_INVALID_ARGUMENT, "field number 0");
-    switch (wire_type) {
-      case 0: value = varint(); break;
-      case 2: {
-        uint64_t n = varint();
-        if (n > (uint64_t)(end_ - p_)) throw WireError("Decode", FHE_B200_INVALID_ARGUMENT, "length overruns the buffer");
-        span.p = p_;
-        span.n = (size_t)n;
-        p_ += n;
-        break;
-      }
-      case 1:
-      case 5: {
-        size_t n = wire_type == 1 ? 8 : 4;
-        if (n > (size_t)(end_ - p_)) throw WireError("Decode", FHE_B200_INVALID_ARGUMENT, "truncated fixed-width field");
-        value = 0;
-        for (size_t i = 0; i < n; i++) value |= (uint64_t)p_[i] << (8 * i);
-        p_ += n;
-        break;
-      }
-      default: throw WireError("Decode", FHE_B200_INVALID_ARGUMENT, "unsupported wire type");
-    }
+    key(field, wire_type);
+    skip_or_read(field, wire_type, 0, true);
     return true;
   }
   void expect(int wt) const {
-    if (wire_type != wt) throw WireError("Decode", FHE_B200_INVALID_ARGUMENT, "unexpected wire type for a known field");
+    if (wire_type != wt) fail("unexpected wire type for a known field");
   }
   uint32_t field = 0;
   int wire_type = 0;
@@ -102,13 +81,66 @@ class Reader {
   Span span;
 
  private:
+  [[noreturn]] static void fail(const char* why) { throw WireError("Decode", FHE_B200_INVALID_ARGUMENT, why); }
   uint64_t varint() {
     uint64_t v = 0;
     for (int shift = 0;; shift += 7) {
-      if (p_ >= end_ || shift > 63) throw WireError("Decode", FHE_B200_INVALID_ARGUMENT, "truncated or overlong varint");
+      if (p_ >= end_) fail("truncated varint");
       uint8_t b = *p_++;
+      if (shift == 63 && b > 1) fail("varint overflows 64 bits");
       v |= (uint64_t)(b & 0x7f) << shift;
       if (!(b & 0x80)) return v;
+    }
+  }
+  void key(uint32_t& f, int& wt) {
+    uint64_t k = varint();
+    if (k > 0xFFFFFFFFull) fail("key does not fit 32 bits");
+    if ((k >> 3) == 0) fail("field number 0");
+    f = (uint32_t)(k >> 3);
+    wt = (int)(k & 7);
+  }
+  void skip_or_read(uint32_t f, int wt, int depth, bool keep) {
+    switch (wt) {
+      case 0: {
+        uint64_t v = varint();
+        if (keep) value = v;
+        break;
+      }
+      case 2: {
+        uint64_t n = varint();
+        if (n > (uint64_t)(end_ - p_)) fail("length overruns the buffer");
+        if (keep) { span.p = p_; span.n = (size_t)n; }
+        p_ += n;
+        break;
+      }
+      case 1:
+      case 5: {
+        size_t n = wt == 1 ? 8 : 4;
+        if (n > (size_t)(end_ - p_)) fail("truncated fixed-width field");
+        if (keep) {
+          value = 0;
+          for (size_t i = 0; i < n; i++) value |= (uint64_t)p_[i] << (8 * i);
+        }
+        p_ += n;
+        break;
+      }
+      case 3: {
+        if (depth >= 100) fail("recursion limit");
+        for (;;) {
+          if (p_ >= end_) fail("unterminated group");
+          uint32_t gf;
+          int gw;
+          key(gf, gw);
+          if (gw == 4) {
+            if (gf != f) fail("mismatched end of group");
+            break;
+          }
+          skip_or_read(gf, gw, depth + 1, false);
+        }
+        if (keep) value = 0;
+        break;
+      }
+      default: fail("unsupported wire type");
     }
   }
   const uint8_t *p_, *end_;

@@ -319,3 +319,72 @@ def test_cpp_codec_matches_protobuf_runtime(ow, tmp_path):
         pos += n
         assert got == want
     assert pos == len(out)
+
+
+def test_codecs_under_mutation(ow, tmp_path):
+    """Mutated Ciphertext messages (bit flips, truncations, insertions, overwritten bytes): the Python and the C++ codec
+    decide and decode identically, and they agree with the google.protobuf runtime except where prost itself differs
+    from it -- a known field that arrives with another wire type is a decode error in prost, an unknown field in the
+    runtime."""
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "wire_codec_test")
+    lib_dir = os.path.join(root, "fhe_rs_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "wire_codec_test.cpp"), "-o", exe,
+                           "-L", lib_dir, "-lfhe_b200", "-Wl,-rpath," + lib_dir])
+    rng = np.random.default_rng(1)
+    cases, verdicts = [], []
+    for _ in range(6000):
+        polys = [_rand_bytes(rng, int(rng.integers(0, 40))) for _ in range(int(rng.integers(2, 4)))]
+        m = bytearray(ow.CiphertextProto(c=polys, seed=b"s" * 32 if rng.integers(0, 2) else b"",
+                                         level=int(rng.integers(0, 300))).SerializeToString())
+        kind, i = int(rng.integers(0, 5)), int(rng.integers(0, len(m)))
+        if kind == 0:
+            m[i] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            m = m[:i]
+        elif kind == 2:
+            m[i:i] = _rand_bytes(rng, int(rng.integers(1, 4)))
+        elif kind == 3:
+            m[i] = int(rng.integers(0, 256))
+        else:                                   # an unknown group, possibly nested / unterminated
+            m[i:i] = [b"\x7b\x78\x01\x7c", b"\x7b\x73\x74\x7c", b"\x7b\x78\x01", b"\x7b\x74", b"\x7c"][int(rng.integers(0, 5))] \
+                if i == 0 else b""
+        m = bytes(m)
+        try:
+            c, seed, level = wire.decode_ciphertext(m)
+            mine = wire.encode_ciphertext(c, seed, level)
+        except WireError as e:
+            mine = e
+        ref = ow.CiphertextProto()
+        try:
+            ref.ParseFromString(m)
+            ok = len(ref.c) >= 2 or (len(ref.c) == 1 and len(ref.seed))      # ciphertext.rs:261-269
+            # canonical form of the known fields (the runtime would carry unknown fields along; prost drops them)
+            theirs = ow.CiphertextProto(c=list(ref.c), seed=ref.seed, level=ref.level).SerializeToString() if ok \
+                else "InvalidCiphertextPolynomialCount"
+        except Exception:  # noqa: BLE001
+            theirs = "Decode"
+        if isinstance(mine, WireError):
+            assert mine.variant == theirs or (mine.variant == "Decode" and "wire type" in str(mine)), (m.hex(), str(mine))
+        else:
+            assert mine == theirs, m.hex()
+        cases.append(b"c" + struct.pack("<I", len(m)) + m)
+        verdicts.append(mine)
+    assert sum(isinstance(v, WireError) for v in verdicts) > 1000 and sum(isinstance(v, bytes) for v in verdicts) > 1000
+    (tmp_path / "in.bin").write_bytes(b"".join(cases))
+    subprocess.check_call([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out, pos = (tmp_path / "out.bin").read_bytes(), 0
+    for mine in verdicts:
+        (n,) = struct.unpack_from("<I", out, pos)
+        pos += 4
+        if n == 0xFFFFFFFF:
+            (n,) = struct.unpack_from("<I", out, pos)
+            pos += 4
+            assert isinstance(mine, WireError) and out[pos:pos + n].decode() == mine.variant
+        else:
+            assert out[pos:pos + n] == mine
+        pos += n
+    assert pos == len(out)
