@@ -20,7 +20,7 @@ see include/fhe_b200.h; `*_from_bytes` take the expanded half from the caller.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional
 
 import numpy as np
 from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
