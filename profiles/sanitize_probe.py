@@ -33,4 +33,8 @@ assert (P[0] == exp.to_array()).all()
 R = F.GaloisKey.from_arrays(gpar, 3, kc[1], kc[0]).relinearize(A).to_host()
 X = F.Ciphertext.from_host(gpar, a)
 assert (X.into_power_basis().into_ntt().to_host() == a).all()
+# power-basis substitute, message pack / unpack (device halves of to_bytes / from_bytes)
+Y = F.Ciphertext.from_host(gpar, a).into_power_basis().substitute(3).into_ntt()
+assert (Y.to_host() == F.Ciphertext.from_host(gpar, a).substitute(3).to_host()).all()
+assert (F.Ciphertext.from_bytes(gpar, A.to_bytes()).to_host() == a).all()
 print("sanitize probe ok", R.shape)
