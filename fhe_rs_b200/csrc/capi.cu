@@ -88,6 +88,8 @@ struct fhe_b200_params {
   // scratch of the batched operations comes from a stream-ordered pool this parameter set owns (the device's default
   // pool, which a host application may be using for its own cudaMallocAsync calls, is left untouched)
   cudaMemPool_t pool = nullptr;
+  // side streams over which ChunkRunner deals the chunks of one batched call (created on first use)
+  mutable cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
   mutable std::mutex mu;
   mutable std::map<u32, std::unique_ptr<LevelData>> levels;
   mutable std::map<u32, int*> perms;
@@ -247,6 +249,8 @@ void params_release(const fhe_b200_params* cp) {
     cudaGetDevice(&prev);
     cudaSetDevice(p->device);
     for (void* d : p->d_allocs) cudaFree(d);
+    for (cudaStream_t ss : p->side)
+      if (ss) cudaStreamDestroy(ss);
     if (p->pool) {
       cudaDeviceSynchronize();   // scratch freed with cudaFreeAsync must have retired before its pool goes away
       cudaMemPoolDestroy(p->pool);
@@ -357,6 +361,61 @@ u32 chunk_size() {
   }();
   return c;
 }
+
+// A batched call works through its ciphertexts chunk by chunk.  On ONE stream every kernel boundary costs ~16 us (tail
+// of one persistent grid, ring fill and table staging of the next: profiles/microbench_r2.txt), 18 boundaries per chunk.
+// When a call has more than one chunk the runner therefore deals the chunks over side streams of the parameter set
+// (two by default, FHE_B200_STREAMS=1..4): the kernels of one chunk fill the SMs that the kernels of another leave at
+// their boundaries, and kernels bound by different resources (integer pipe, HBM) share an SM.  The caller's stream is the
+// only one it ever sees: the side streams start behind an event recorded on it and it waits for all of them before the
+// call returns.  Each side stream works on chunks of chunk_size() / streams ciphertexts, so the scratch in flight is what
+// one full chunk takes.  FHE_B200_STREAMS=1 keeps everything on the caller's stream.
+struct ChunkRunner {
+  const fhe_b200_params* par;
+  cudaStream_t user;
+  u32 count, chunk, ns;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  static u32 streams() {
+    static const u32 n = [] {
+      const char* e = getenv("FHE_B200_STREAMS");
+      const int v = e ? atoi(e) : 2;
+      return (u32)(v < 1 ? 1 : v > 4 ? 4 : v);
+    }();
+    return n;
+  }
+  ChunkRunner(const fhe_b200_params* p, u32 n, cudaStream_t st) : par(p), user(st), count(n), chunk(chunk_size()), ns(1) {
+    if (streams() < 2 || count <= chunk || chunk < streams()) return;
+    ns = streams();
+    chunk = (chunk + ns - 1) / ns;
+    {
+      std::lock_guard<std::mutex> g(par->mu);
+      for (u32 i = 0; i < ns; i++)
+        if (!par->side[i]) FHE_CUDA(cudaStreamCreateWithFlags(&par->side[i], cudaStreamNonBlocking));
+    }
+    for (u32 i = 0; i <= ns; i++) FHE_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    FHE_CUDA(cudaEventRecord(ev[ns], user));
+    for (u32 i = 0; i < ns; i++) FHE_CUDA(cudaStreamWaitEvent(par->side[i], ev[ns], 0));
+  }
+  // body(first ciphertext, number of ciphertexts, stream)
+  template <class F>
+  void run(F&& body) {
+    u32 k = 0;
+    for (u32 c0 = 0; c0 < count; c0 += chunk, k++) body(c0, std::min(chunk, count - c0), ns > 1 ? par->side[k % ns] : user);
+    join();
+  }
+  void join() {
+    if (ns < 2 || joined) return;
+    joined = true;
+    for (u32 i = 0; i < ns; i++)
+      if (cudaEventRecord(ev[i], par->side[i]) == cudaSuccess) cudaStreamWaitEvent(user, ev[i], 0);
+  }
+  ~ChunkRunner() {
+    join();                         // also when a chunk failed half way: the caller's stream still has to wait
+    for (cudaEvent_t e : ev)
+      if (e) cudaEventDestroy(e);   // released once the recorded work has completed
+  }
+  bool joined = false;
+};
 
 void check_same(const fhe_b200_batch* a, const fhe_b200_batch* b) {
   if (a->par != b->par) throw FheError(FHE_B200_CONTEXT_MISMATCH, "ParameterMismatch: batches use different parameters");
@@ -1031,10 +1090,9 @@ int fhe_b200_mul_relin(const fhe_b200_batch* a, const fhe_b200_batch* b, const f
     REQUIRE(out2->level == a->level, FHE_B200_INVALID_LEVEL, "output batch must be at the operand level");
   }
   DeviceGuard g(par);
-  cudaStream_t st = (cudaStream_t)stream;
   const size_t row = (size_t)1 << par->logn, L = lv.L;
-  for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
-    u32 n = std::min(chunk_size(), a->count - c0);
+  ChunkRunner chunks(par, a->count, (cudaStream_t)stream);
+  chunks.run([&](u32 c0, u32 n, cudaStream_t st) {
     Workspace ws(par, st);
     u64* o = mod_switch ? ws.words((size_t)n * 2 * L * row) : out2->d + (size_t)c0 * 2 * L * row;
     u64* c2 = ws.words((size_t)n * L * row);
@@ -1050,7 +1108,7 @@ int fhe_b200_mul_relin(const fhe_b200_batch* a, const fhe_b200_batch* b, const f
       const LevelData& nl = par->level(a->level + 1);
       launch_ntt(dst, dst, n * 2 * (u32)(L - 1), nl.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
     }
-  }
+  });
   FHE_CUDA(cudaGetLastError());
   out2->repr = FHE_B200_NTT;
   API_END
@@ -1238,12 +1296,11 @@ int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_
   exponent %= 2 * par->N;
   REQUIRE(exponent & 1, FHE_B200_INVALID_EXPONENT, "InvalidSubstitutionExponent");
   DeviceGuard g(par);
-  cudaStream_t st = (cudaStream_t)stream;
   const LevelData& lv = par->level(ct->level);
   const size_t row = (size_t)1 << par->logn, L = lv.L;
   const int* perm = par->perm(exponent);
-  for (u32 c0 = 0; c0 < ct->count; c0 += chunk_size()) {
-    u32 n = std::min(chunk_size(), ct->count - c0);
+  ChunkRunner chunks(par, ct->count, (cudaStream_t)stream);
+  chunks.run([&](u32 c0, u32 n, cudaStream_t st) {
     Workspace ws(par, st);
     const u64* src = ct->d + (size_t)c0 * 2 * L * row;
     u64* dst = out->d + (size_t)c0 * 2 * L * row;
@@ -1255,7 +1312,7 @@ int fhe_b200_galois(const fhe_b200_batch* ct, uint32_t exponent, const fhe_b200_
     launch_ntt(c2, c2, n * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
     // galois_key.rs:67 + :78: out0 = key_switch0 + substitute(ct[0]); out1 = key_switch1
     key_switch_apply(par, gk, c2, n, dst, 2, s, ws, st);
-  }
+  });
   FHE_CUDA(cudaGetLastError());
   out->repr = FHE_B200_NTT;
   API_END
