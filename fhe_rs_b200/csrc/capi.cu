@@ -1011,13 +1011,13 @@ int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batc
   need_repr(a, FHE_B200_NTT);
   need_repr(b, FHE_B200_NTT);
   DeviceGuard g(a->par);
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st_user = (cudaStream_t)stream;
   const fhe_b200_params* par = a->par;
   const LevelData& lv = par->level(a->level);
   const size_t row = (size_t)1 << par->logn;
   const u32 na = a->parts, nb = b->parts, nc = na + nb - 1;
-  for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
-    u32 n = std::min(chunk_size(), a->count - c0);
+  ChunkRunner chunks(par, a->count, st_user);
+  chunks.run([&](u32 c0, u32 n, cudaStream_t st) {
     Workspace ws(par, st);
     u64* o = out3->d + (size_t)c0 * nc * lv.L * row;
     const u64* pa = a->d + (size_t)c0 * na * lv.L * row;
@@ -1026,7 +1026,7 @@ int fhe_b200_mul(const fhe_b200_batch* a, const fhe_b200_batch* b, fhe_b200_batc
     else mul_core_parts(par, lv, pa, na, pb, nb, n, o, ws, st);
     // rq/scaler.rs:97-115 forward NTT of the scaled result
     launch_ntt(o, o, n * nc * lv.L, lv.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
-  }
+  });
   FHE_CUDA(cudaGetLastError());
   out3->repr = FHE_B200_NTT;
   API_END
@@ -1047,12 +1047,12 @@ int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_
   need_repr(ct3, FHE_B200_NTT);
   check_ksk(rk, ct3->par, ct3->level);
   DeviceGuard g(ct3->par);
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st_user = (cudaStream_t)stream;
   const fhe_b200_params* par = ct3->par;
   const LevelData& lv = par->level(ct3->level);
   const size_t row = (size_t)1 << par->logn, L = lv.L;
-  for (u32 c0 = 0; c0 < ct3->count; c0 += chunk_size()) {
-    u32 n = std::min(chunk_size(), ct3->count - c0);
+  ChunkRunner chunks(par, ct3->count, st_user);
+  chunks.run([&](u32 c0, u32 n, cudaStream_t st) {
     Workspace ws(par, st);
     const u64* src = ct3->d + (size_t)c0 * 3 * L * row;
     u64* dst = out2->d + (size_t)c0 * 2 * L * row;
@@ -1062,7 +1062,7 @@ int fhe_b200_relinearize(const fhe_b200_batch* ct3, const fhe_b200_ksk* rk, fhe_
     // relinearization_key.rs:85: c2 -> power basis
     launch_ntt(c2, c2, n * (u32)L, lv.ctx_ids, par->d_limbs, par->logn, true, 1, false, st);
     key_switch_apply(par, rk, c2, n, dst, 1, nullptr, ws, st);
-  }
+  });
   FHE_CUDA(cudaGetLastError());
   out2->repr = FHE_B200_NTT;
   API_END
@@ -1230,10 +1230,9 @@ int fhe_b200_multiplicator_multiply(const fhe_b200_multiplicator* m, const fhe_b
     REQUIRE(out->level == m->level, FHE_B200_INVALID_LEVEL, "output batch must be at the operand level");
   }
   DeviceGuard g(par);
-  cudaStream_t st = (cudaStream_t)stream;
   const size_t row = (size_t)1 << par->logn, L = lv.L;
-  for (u32 c0 = 0; c0 < a->count; c0 += chunk_size()) {
-    const u32 n = std::min(chunk_size(), a->count - c0);
+  ChunkRunner chunks(par, a->count, (cudaStream_t)stream);
+  chunks.run([&](u32 c0, u32 n, cudaStream_t st) {
     Workspace ws(par, st);
     const bool direct = !rk && !mod_switch;
     u64* W = direct ? out->d + (size_t)c0 * 3 * L * row : ws.words((size_t)n * 3 * L * row);
@@ -1257,7 +1256,7 @@ int fhe_b200_multiplicator_multiply(const fhe_b200_multiplicator* m, const fhe_b
       const LevelData& nl = par->level(m->level + 1);
       launch_ntt(dst, dst, n * out_parts * (u32)(L - 1), nl.ctx_ids, par->d_limbs, par->logn, false, 1, false, st);
     }
-  }
+  });
   FHE_CUDA(cudaGetLastError());
   out->repr = FHE_B200_NTT;
   API_END
@@ -1330,17 +1329,17 @@ int fhe_b200_key_switch(const fhe_b200_batch* pb, uint32_t part, const fhe_b200_
   need_repr(pb, FHE_B200_POWER_BASIS);
   const fhe_b200_params* par = pb->par;
   DeviceGuard g(par);
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st_user = (cudaStream_t)stream;
   const size_t row = (size_t)1 << par->logn, L = pb->limbs, Lk = k->Lk;
-  for (u32 c0 = 0; c0 < pb->count; c0 += chunk_size()) {
-    u32 n = std::min(chunk_size(), pb->count - c0);
+  ChunkRunner chunks(par, pb->count, st_user);
+  chunks.run([&](u32 c0, u32 n, cudaStream_t st) {
     Workspace ws(par, st);
     u64* c2 = ws.words((size_t)n * L * row);
     FHE_CUDA(cudaMemcpy2DAsync(c2, L * row * 8, pb->d + ((size_t)c0 * pb->parts + part) * L * row,
                                pb->parts * L * row * 8, L * row * 8, n, cudaMemcpyDeviceToDevice, st));
     u64* dst = out2->d + (size_t)c0 * 2 * Lk * row;
     key_switch_core(par, k, c2, n, nullptr, nullptr, dst, dst + Lk * row, 2 * (u32)Lk, ws, st);
-  }
+  });
   FHE_CUDA(cudaGetLastError());
   out2->repr = FHE_B200_NTT;
   API_END

@@ -1001,3 +1001,18 @@ def test_messages_against_oracle(oracle, F, degree, nmod):
         data = ow.CiphertextProto(c=[ow.poly_to_bytes(p) for p in short], level=last).SerializeToString()
         got = F.Ciphertext.from_bytes(gpar, [data])
         assert (got.to_host()[0] == ow.ciphertext_from_bytes(opar, data).to_array()).all()
+
+
+@pytest.mark.parametrize("env", [{"FHE_B200_CHUNK": "2"}, {"FHE_B200_CHUNK": "3", "FHE_B200_STREAMS": "3"},
+                                 {"FHE_B200_CHUNK": "4", "FHE_B200_STREAMS": "4"}, {"FHE_B200_CHUNK": "2", "FHE_B200_STREAMS": "1"}])
+def test_chunk_runner_entry_points(F, env):
+    """capi.cu::ChunkRunner: a batched call deals its chunks over side streams of the parameter set; every chunked entry
+    point, on a batch of several chunks, equals the same call on one-ciphertext batches (tests/chunk_runner_probe.py).
+    Oracle parity across the chunk boundary at the benchmarked size is test_set_c_across_chunk_boundary."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "chunk_runner_probe.py")], cwd=root,
+                         env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "chunk runner probe ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
