@@ -21,7 +21,11 @@
  *    after creation and may be shared by host threads (like Arc<BfvParameters>,
  *    bfv/parameters.rs:125); a batch handle must not be mutated concurrently.
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Work is
- *    enqueued asynchronously; fhe_b200_sync() or a download waits for it.
+ *    enqueued asynchronously; fhe_b200_sync() or a download waits for it.  `stream` is the only
+ *    stream the caller has to reason about: a batched operation over more ciphertexts than one chunk
+ *    (FHE_B200_CHUNK, default 256) runs its chunks on side streams owned by the parameter set, but
+ *    these start behind everything already enqueued on `stream` and `stream` waits for them before
+ *    the call returns, so the operation is ordered on `stream` like a single kernel would be.
  *  - host layout of a batch == Vec<u64>::from(&Poly) of the reference
  *    (rq/convert.rs:474-503) concatenated over parts and ciphertexts:
  *    [ciphertext][part][limb][coefficient], row-major, limb i modulo moduli[i].
