@@ -5,6 +5,7 @@
 //   bfv::BfvParameters / BfvParametersBuilder   bfv/parameters.rs:88, :319
 //   bfv::Ciphertext                             bfv/ciphertext.rs:18  (here: a device-resident batch)
 //   bfv::KeySwitchingKey / RelinearizationKey   bfv/keys/key_switching_key.rs:22, relinearization_key.rs:23
+//   bfv::RGSWCiphertext                         bfv/rgsw_ciphertext.rs:20 (external product = two key switches)
 //   bfv::GaloisKey / EvaluationKey              bfv/keys/galois_key.rs:18, evaluation_key.rs:110-170
 //   bfv::Multiplicator                          bfv/ops/mul.rs:22
 // Fallible reference calls return Result<_, fhe::Error>; here they throw fhe_b200::Error carrying
@@ -152,7 +153,7 @@ class Ciphertext {
   size_t words() const { return (size_t)count() * len() * limbs() * par_->degree(); }
 
   Ciphertext clone() const {
-    Ciphertext c(par_, count(), len(), level(), Representation::Ntt, stream_);
+    Ciphertext c(par_, count(), len(), level(), representation(), stream_);
     check(fhe_b200_batch_copy(c.h_, h_, stream_));
     return c;
   }
@@ -175,6 +176,20 @@ class Ciphertext {
   Ciphertext& mul_plain(const std::vector<uint64_t>& poly_ntt) {
     check(fhe_b200_mul_plain(h_, poly_ntt.data(), 1, stream_));
     return *this;
+  }
+  // Poly::into_ntt / into_power_basis on every polynomial (rq/mod.rs:535, :590)
+  Ciphertext& into_ntt() { check(fhe_b200_ntt_forward(h_, stream_)); return *this; }
+  Ciphertext& into_power_basis() { check(fhe_b200_ntt_backward(h_, stream_)); return *this; }
+  Representation representation() const {
+    int r;
+    check(fhe_b200_batch_info(h_, nullptr, nullptr, nullptr, nullptr, &r));
+    return (Representation)r;
+  }
+  // Poly::substitute on every polynomial, in either representation (rq/mod.rs:360-408)
+  Ciphertext substitute(uint32_t exponent) const {
+    Ciphertext out(par_, count(), len(), level(), representation(), stream_);
+    check(fhe_b200_substitute(h_, exponent, out.h_, stream_));
+    return out;
   }
   // Ciphertext::switch_down (bfv/ciphertext.rs:148)
   void switch_down() { check(fhe_b200_switch_down(h_, stream_)); }
@@ -228,6 +243,14 @@ class KeySwitchingKey {
   ~KeySwitchingKey() { fhe_b200_ksk_free(h_); }
   const fhe_b200_ksk* handle() const { return h_; }
   uint32_t ciphertext_level() const { return ciphertext_level_; }
+  uint32_t ksk_level() const { return ksk_level_; }
+  // KeySwitchingKey::key_switch (key_switching_key.rs:241-270, :323-362) on polynomial `part` of a power-basis batch:
+  // the (c0, c1) pair as a 2-part NTT batch at the key level
+  Ciphertext key_switch(const Ciphertext& p, uint32_t part = 0) const {
+    Ciphertext out(par_, p.count(), 2, ksk_level_, Representation::Ntt, p.stream());
+    check(fhe_b200_key_switch(p.handle(), part, h_, out.handle(), p.stream()));
+    return out;
+  }
   const std::shared_ptr<BfvParameters>& par() const { return par_; }
 
  private:
@@ -262,6 +285,27 @@ class GaloisKey {
 };
 
 // rotation subset of EvaluationKey (evaluation_key.rs:110-170)
+// fhe::bfv::RGSWCiphertext (bfv/rgsw_ciphertext.rs:20-24): two key-switching keys (for m and m*s) of one level
+class RGSWCiphertext {
+ public:
+  RGSWCiphertext(std::shared_ptr<KeySwitchingKey> k0, std::shared_ptr<KeySwitchingKey> k1) : ksk0(std::move(k0)), ksk1(std::move(k1)) {
+    if (ksk0->ksk_level() != ksk0->ciphertext_level() || ksk1->ksk_level() != ksk1->ciphertext_level() ||
+        ksk0->ciphertext_level() != ksk1->ciphertext_level())
+      throw Error(FHE_B200_INVALID_LEVEL, "InconsistentKeySwitchingLevels");   // rgsw_ciphertext.rs:58-70
+  }
+  // &Ciphertext * &RGSWCiphertext (rgsw_ciphertext.rs:122-155): key-switch both parts, add
+  Ciphertext external_product(const Ciphertext& ct) const {
+    if (ct.level() != ksk0->ciphertext_level()) throw Error(FHE_B200_INVALID_LEVEL, "Ciphertext and RGSWCiphertext must have the same level");
+    if (ct.len() != 2) throw Error(FHE_B200_BAD_POLY_COUNT, "Ciphertext must have two parts");
+    Ciphertext pb = ct.clone();
+    pb.into_power_basis();
+    Ciphertext out = ksk0->key_switch(pb, 0);
+    out += ksk1->key_switch(pb, 1);
+    return out;
+  }
+  std::shared_ptr<KeySwitchingKey> ksk0, ksk1;
+};
+
 class EvaluationKey {
  public:
   explicit EvaluationKey(std::shared_ptr<BfvParameters> par) : par_(std::move(par)) {}
