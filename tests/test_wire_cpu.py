@@ -266,6 +266,8 @@ def test_cpp_codec_matches_protobuf_runtime(ow, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "wire_codec_test")
     lib_dir = os.path.join(root, "fhe_rs_b200")
+    from fhe_rs_b200 import build
+    build.build()                               # the header links against the C ABI library (no-op when it is current)
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"),
                            os.path.join(root, "tests", "cpp", "wire_codec_test.cpp"), "-o", exe,
                            "-L", lib_dir, "-lfhe_b200", "-Wl,-rpath," + lib_dir])
@@ -331,6 +333,8 @@ def test_codecs_under_mutation(ow, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "wire_codec_test")
     lib_dir = os.path.join(root, "fhe_rs_b200")
+    from fhe_rs_b200 import build
+    build.build()                               # the header links against the C ABI library (no-op when it is current)
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"),
                            os.path.join(root, "tests", "cpp", "wire_codec_test.cpp"), "-o", exe,
                            "-L", lib_dir, "-lfhe_b200", "-Wl,-rpath," + lib_dir])
